@@ -1,0 +1,477 @@
+// C ABI of libhhe_b200.so (include/hhe_b200.h): host-buffer marshalling around hhe::Engine.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hhe_b200.h"
+#include "engine.h"
+
+using namespace hhe;
+
+struct hhe_ctx {
+  std::unique_ptr<Engine> eng;
+};
+
+namespace {
+
+thread_local std::string g_error;
+
+template <class F>
+int guarded(F &&f) {
+  try {
+    f();
+    return HHE_OK;
+  } catch (const std::invalid_argument &e) {
+    g_error = e.what();
+    return HHE_ERR_INVALID;
+  } catch (const std::logic_error &e) {
+    g_error = e.what();
+    return HHE_ERR_LOGIC;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return g_error.rfind("NO_DEVICE", 0) == 0 ? HHE_ERR_NO_DEVICE : HHE_ERR_RUNTIME;
+  }
+}
+
+Engine &E(hhe_ctx *c) {
+  if (!c || !c->eng) throw std::invalid_argument("null context");
+  return *c->eng;
+}
+
+u64 *up(Engine &e, const u64 *host, size_t words) {
+  u64 *d = e.scratch(words);
+  e.dev().h2d(d, host, words * 8);
+  return d;
+}
+
+void down(Engine &e, u64 *host, const u64 *d, size_t words) { e.dev().d2h(host, d, words * 8); }
+
+// run `fn(first, n)` over [0, count) in chunks of the engine's batch limit
+template <class F>
+void chunked(Engine &e, size_t count, F &&fn) {
+  const size_t step = static_cast<size_t>(std::max(1, e.batch_limit()));
+  for (size_t off = 0; off < count; off += step) fn(off, std::min(step, count - off));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hhe_last_error(void) { return g_error.c_str(); }
+const char *hhe_version(void) { return "hhe_b200 0.1 (sm_100a)"; }
+
+int hhe_ctx_create(hhe_ctx **out, uint64_t N, uint64_t t, const uint64_t *q, int nq, int device, void *stream) {
+  if (!out) return HHE_ERR_INVALID;
+  *out = nullptr;
+  return guarded([&] {
+    Params p = Params::derive(N, t, q, nq);
+    auto ctx = std::make_unique<hhe_ctx>();
+    ctx->eng = std::make_unique<Engine>(p, device, stream);
+    *out = ctx.release();
+  });
+}
+
+void hhe_ctx_destroy(hhe_ctx *ctx) { delete ctx; }
+
+int hhe_ctx_info(const hhe_ctx *ctx, uint64_t *info) {
+  return guarded([&] {
+    Engine &e = E(const_cast<hhe_ctx *>(ctx));
+    info[0] = e.params().N;
+    info[1] = e.params().L;
+    info[2] = e.params().K;
+    info[3] = e.params().t;
+    info[4] = e.batch_limit();
+    info[5] = e.dev().sm_count;
+  });
+}
+
+void *hhe_ctx_stream(const hhe_ctx *ctx) {
+#ifdef HHE_CUDA
+  return ctx && ctx->eng ? static_cast<void *>(ctx->eng->dev().stream) : nullptr;
+#else
+  (void)ctx;
+  return nullptr;
+#endif
+}
+
+int hhe_set_batch(hhe_ctx *ctx, int blocks) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (blocks < 0) throw std::invalid_argument("batch must be >= 0");
+    e.set_batch(blocks ? blocks : 2 * e.dev().sm_count);
+  });
+}
+
+uint32_t hhe_galois_elt(const hhe_ctx *ctx, int step) {
+  return ctx && ctx->eng ? ctx->eng->params().galois_elt_from_step(step) : 0;
+}
+
+int hhe_ctx_constants(const hhe_ctx *ctx, uint64_t *out) {
+  return guarded([&] {
+    const Params &p = E(const_cast<hhe_ctx *>(ctx)).params();
+    size_t o = 0;
+    for (int i = 0; i < p.K; ++i) out[o++] = p.tab[i].psi;
+    out[o++] = p.tab[p.tab_plain()].psi;
+    out[o++] = p.m_sk;
+    out[o++] = p.gamma;
+    out[o++] = p.m_tilde;
+    for (int i = 0; i < p.L; ++i) out[o++] = p.bsk[i];
+    for (int i = 0; i <= p.L; ++i) out[o++] = p.tab[p.tab_bsk(i)].psi;
+  });
+}
+
+int hhe_load_ksk(hhe_ctx *ctx, int kind, uint32_t galois_elt, const uint64_t *ksk) {
+  return guarded([&] {
+    if (!ksk) throw std::invalid_argument("null key");
+    E(ctx).load_ksk(kind, galois_elt, ksk);
+  });
+}
+
+int hhe_has_ksk(const hhe_ctx *ctx, int kind, uint32_t galois_elt) {
+  return ctx && ctx->eng && ctx->eng->find_key(kind, galois_elt) ? 1 : 0;
+}
+
+uint64_t hhe_launch_count(const hhe_ctx *ctx) { return ctx && ctx->eng ? ctx->eng->dev().launches : 0; }
+
+// ---------------------------------------------------------------------------------------------- primitives
+int hhe_ntt(hhe_ctx *ctx, int limb, int inverse, uint64_t *data, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    const Params &p = e.params();
+    if (limb < 0 || limb >= 2 * p.K) throw std::invalid_argument("limb index out of range");
+    Engine::Scope sc(e);
+    const size_t words = count * p.N;
+    u64 *d = up(e, data, words);
+    TabMap m{};
+    m.id[0] = static_cast<unsigned char>(limb);
+    e.ntt(d, d, count, 1, m, inverse != 0);
+    down(e, data, d, words);
+    e.dev().sync();
+  });
+}
+
+int hhe_encode(hhe_ctx *ctx, const uint64_t *slots, size_t n_slots, uint64_t *pt, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    const Params &p = e.params();
+    if (n_slots > p.N) throw std::invalid_argument("values_matrix size exceeds slot count");
+    for (size_t i = 0; i < n_slots * count; ++i)
+      if (slots[i] >= p.t) throw std::invalid_argument("input value is larger than plain_modulus");
+    Engine::Scope sc(e);
+    u64 *ds = up(e, slots, std::max<size_t>(1, n_slots * count));
+    u64 *dp = e.scratch(count * p.N);
+    e.encode_slots(ds, n_slots, nullptr, static_cast<u32>(n_slots), dp, count);
+    down(e, pt, dp, count * p.N);
+    e.dev().sync();
+  });
+}
+
+int hhe_add(hhe_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w), *db = up(e, b, w);
+    e.add(da, db, da, count);
+    down(e, out, da, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_negate(hhe_ctx *ctx, const uint64_t *a, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w);
+    e.negate(da, da, count);
+    down(e, out, da, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_add_plain(hhe_ctx *ctx, const uint64_t *a, const uint64_t *pt, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words(), N = e.params().N;
+    u64 *da = up(e, a, w), *dp = up(e, pt, count * N);
+    e.add_plain(da, dp, N, da, count, false);
+    down(e, out, da, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_multiply_plain(hhe_ctx *ctx, const uint64_t *a, const uint64_t *pt, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words(), N = e.params().N;
+    for (size_t it = 0; it < count; ++it) {
+      bool zero = true;
+      for (size_t j = 0; j < N && zero; ++j) zero = pt[it * N + j] == 0;
+      if (zero) throw std::logic_error("result ciphertext is transparent");
+    }
+    u64 *da = up(e, a, w), *dp = up(e, pt, count * N), *dout = e.scratch(w);
+    e.multiply_plain(da, dp, N, dout, count);
+    down(e, out, dout, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_rotate_rows(hhe_ctx *ctx, const uint64_t *a, int steps, int keyset, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w), *dout = e.scratch(w);
+    e.rotate_rows(da, steps, keyset, dout, count);
+    down(e, out, dout, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_rotate_columns(hhe_ctx *ctx, const uint64_t *a, int keyset, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w), *dout = e.scratch(w);
+    e.rotate_columns(da, keyset, dout, count);
+    down(e, out, dout, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_multiply(hhe_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w), *db = (a == b) ? da : up(e, b, w), *dout = e.scratch(count * e.ct_words(3));
+    e.multiply(da, db, dout, count);
+    down(e, out3, dout, count * e.ct_words(3));
+    e.dev().sync();
+  });
+}
+
+int hhe_square(hhe_ctx *ctx, const uint64_t *a, uint64_t *out3, size_t count) { return hhe_multiply(ctx, a, a, out3, count); }
+
+int hhe_relinearize(hhe_ctx *ctx, const uint64_t *a3, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    u64 *da = up(e, a3, count * e.ct_words(3)), *dout = e.scratch(count * e.ct_words());
+    e.relinearize(da, dout, count);
+    down(e, out, dout, count * e.ct_words());
+    e.dev().sync();
+  });
+}
+
+int hhe_exponentiate3(hhe_ctx *ctx, const uint64_t *a, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w), *dout = e.scratch(w);
+    e.exponentiate3(da, dout, count);
+    down(e, out, dout, w);
+    e.dev().sync();
+  });
+}
+
+// ---------------------------------------------------------------------------------------------- hot path
+static void decompose_host(Engine &e, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words, size_t records,
+                           uint64_t nonce, uint64_t first_counter, int use_bsgs, uint64_t *out) {
+  const Params &p = e.params();
+  if (!enc_key || !sym_ct || !out) throw std::invalid_argument("null buffer");
+  if (n_words == 0 || records == 0) return;
+  for (size_t i = 0; i < n_words * records; ++i)
+    if (sym_ct[i] >= p.t) throw std::invalid_argument("input value is larger than plain_modulus");
+  const size_t bpr = (n_words + kPastaT - 1) / kPastaT, nblocks = bpr * records;
+  std::vector<u64> sym(nblocks * kPastaT, 0), counters(nblocks);
+  std::vector<u32> lens(nblocks);
+  for (size_t r = 0; r < records; ++r)
+    for (size_t b = 0; b < bpr; ++b) {
+      const size_t cnt = std::min<size_t>(kPastaT, n_words - b * kPastaT), blk = r * bpr + b;
+      std::memcpy(&sym[blk * kPastaT], sym_ct + r * n_words + b * kPastaT, cnt * 8);
+      lens[blk] = static_cast<u32>(cnt);
+      counters[blk] = first_counter + b;
+    }
+  Engine::Scope sc(e);
+  const size_t ctw = e.ct_words();
+  u64 *d_key = up(e, enc_key, ctw);
+  chunked(e, nblocks, [&](size_t off, size_t nb) {
+    Engine::Scope inner(e);
+    u64 *d_sym = up(e, &sym[off * kPastaT], nb * kPastaT);
+    u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nb + 1) / 2));
+    e.dev().h2d(d_lens, &lens[off], nb * 4);
+    u64 *d_out = e.scratch(nb * ctw);
+    std::vector<u64> ctr(counters.begin() + off, counters.begin() + off + nb);
+    e.pasta_decompose(d_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_out);
+    down(e, out + off * ctw, d_out, nb * ctw);
+    e.dev().sync();
+  });
+}
+
+int hhe_pasta3_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words, uint64_t nonce,
+                         uint64_t first_counter, int use_bsgs, uint64_t *out) {
+  return guarded([&] { decompose_host(E(ctx), enc_key, sym_ct, n_words, 1, nonce, first_counter, use_bsgs, out); });
+}
+
+int hhe_pasta3_decompose_records(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words,
+                                 size_t records, uint64_t nonce, uint64_t first_counter, int use_bsgs, uint64_t *out) {
+  return guarded([&] { decompose_host(E(ctx), enc_key, sym_ct, n_words, records, nonce, first_counter, use_bsgs, out); });
+}
+
+int hhe_mask(hhe_ctx *ctx, const uint64_t *a, const uint64_t *mask, size_t n_mask, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (n_mask > e.params().N) throw std::invalid_argument("values_matrix size exceeds slot count");
+    bool zero = true;
+    for (size_t i = 0; i < n_mask; ++i) {
+      if (mask[i] >= e.params().t) throw std::invalid_argument("input value is larger than plain_modulus");
+      zero = zero && mask[i] == 0;
+    }
+    if (zero) throw std::logic_error("result ciphertext is transparent");
+    Engine::Scope sc(e);
+    const size_t w = count * e.ct_words();
+    u64 *da = up(e, a, w), *dm = up(e, mask, std::max<size_t>(1, n_mask)), *dout = e.scratch(w);
+    e.mask(da, dm, static_cast<u32>(n_mask), dout, count);
+    down(e, out, dout, w);
+    e.dev().sync();
+  });
+}
+
+int hhe_flatten(hhe_ctx *ctx, const uint64_t *in, size_t per, int keyset, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (per == 0) throw std::invalid_argument("flatten needs at least one ciphertext per group");
+    Engine::Scope sc(e);
+    const size_t ctw = e.ct_words();
+    u64 *din = up(e, in, count * per * ctw), *dout = e.scratch(count * ctw);
+    e.flatten(din, per, keyset, dout, count);
+    down(e, out, dout, count * ctw);
+    e.dev().sync();
+  });
+}
+
+int hhe_vec_sum(hhe_ctx *ctx, const uint64_t *a, size_t n, int keyset, uint64_t *out, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    const size_t ctw = e.ct_words();
+    chunked(e, count, [&](size_t off, size_t nb) {
+      Engine::Scope sc(e);
+      u64 *da = up(e, a + off * ctw, nb * ctw), *dout = e.scratch(nb * ctw);
+      e.vec_sum(da, n, keyset, dout, nb);
+      down(e, out + off * ctw, dout, nb * ctw);
+      e.dev().sync();
+    });
+  });
+}
+
+int hhe_fc_rows(hhe_ctx *ctx, const uint64_t *x, size_t samples, const uint64_t *w, size_t rows, size_t n, int keyset,
+                uint64_t *out) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    const size_t ctw = e.ct_words();
+    Engine::Scope sc(e);
+    u64 *dw = up(e, w, rows * ctw);
+    // items are (sample, row) pairs; chunk over samples so a chunk holds whole rows-groups
+    const size_t per_chunk = std::max<size_t>(1, static_cast<size_t>(e.batch_limit()) / std::max<size_t>(1, rows));
+    for (size_t s0 = 0; s0 < samples; s0 += per_chunk) {
+      const size_t ns = std::min(per_chunk, samples - s0), items = ns * rows;
+      Engine::Scope inner(e);
+      u64 *dx = up(e, x + s0 * ctw, ns * ctw);
+      u64 *A = e.scratch(items * ctw), *B = e.scratch(items * ctw), *t3 = e.scratch(items * e.ct_words(3));
+      for (size_t s = 0; s < ns; ++s) {
+        e.broadcast(dx + s * ctw, A + s * rows * ctw, ctw, rows);
+        e.dev().d2d(B + s * rows * ctw, dw, rows * ctw * 8);
+      }
+      e.multiply(A, B, t3, items);   // sealhelper::packed_enc_multiply
+      e.relinearize(t3, A, items);   // Evaluator::relinearize_inplace
+      e.vec_sum(A, n, keyset, B, items);  // sealhelper::encrypted_vec_sum
+      down(e, out + s0 * rows * ctw, B, items * ctw);
+      e.dev().sync();
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------- device-resident API
+int hhe_dev_alloc(hhe_ctx *ctx, size_t bytes, void **dptr) {
+  return guarded([&] { *dptr = E(ctx).dev().dmalloc(bytes); });
+}
+int hhe_dev_free(hhe_ctx *ctx, void *dptr) {
+  return guarded([&] { E(ctx).dev().dfree(dptr); });
+}
+int hhe_dev_upload(hhe_ctx *ctx, void *dptr, const void *host, size_t bytes) {
+  return guarded([&] {
+    E(ctx).dev().h2d(dptr, host, bytes);
+    E(ctx).dev().sync();
+  });
+}
+int hhe_dev_download(hhe_ctx *ctx, void *host, const void *dptr, size_t bytes) {
+  return guarded([&] {
+    E(ctx).dev().d2h(host, dptr, bytes);
+    E(ctx).dev().sync();
+  });
+}
+int hhe_sync(hhe_ctx *ctx) {
+  return guarded([&] { E(ctx).dev().sync(); });
+}
+
+int hhe_dev_ntt(hhe_ctx *ctx, int limb, int inverse, uint64_t *d_data, size_t count) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (limb < 0 || limb >= 2 * e.params().K) throw std::invalid_argument("limb index out of range");
+    TabMap m{};
+    m.id[0] = static_cast<unsigned char>(limb);
+    e.ntt(d_data, d_data, count, 1, m, inverse != 0);
+  });
+}
+
+int hhe_dev_rotate_rows(hhe_ctx *ctx, const uint64_t *d_a, int steps, int keyset, uint64_t *d_out, size_t count) {
+  return guarded([&] { E(ctx).rotate_rows(d_a, steps, keyset, d_out, count); });
+}
+
+int hhe_dev_relinearize(hhe_ctx *ctx, const uint64_t *d_a3, uint64_t *d_out, size_t count) {
+  return guarded([&] { E(ctx).relinearize(d_a3, d_out, count); });
+}
+
+int hhe_dev_multiply(hhe_ctx *ctx, const uint64_t *d_a, const uint64_t *d_b, uint64_t *d_out3, size_t count) {
+  return guarded([&] { E(ctx).multiply(d_a, d_b, d_out3, count); });
+}
+
+int hhe_dev_pasta3_decompose(hhe_ctx *ctx, const uint64_t *d_enc_key, const uint64_t *d_sym, const uint32_t *lens,
+                             const uint64_t *counters, size_t nblocks, uint64_t nonce, int use_bsgs, uint64_t *d_out) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    Engine::Scope sc(e);
+    u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nblocks + 1) / 2));
+    e.dev().h2d(d_lens, lens, nblocks * 4);
+    std::vector<u64> ctr(counters, counters + nblocks);
+    e.pasta_decompose(d_enc_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_out);
+  });
+}
+
+int hhe_pasta_layer_material(hhe_ctx *ctx, uint64_t nonce, uint64_t counter, int layer, uint32_t *mat1, uint32_t *mat2,
+                             uint32_t *rc) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (layer < 0 || layer > 3) throw std::invalid_argument("layer must be 0..3");
+    Engine::Scope sc(e);
+    u64 *d_ctr = up(e, &counter, 1);
+    u32 *d_mat = reinterpret_cast<u32 *>(e.scratch((kMaterialWords + 1) / 2));
+    e.material(d_ctr, 1, nonce, d_mat);
+    const size_t mw = static_cast<size_t>(kPastaT) * kPastaT;
+    e.dev().d2h(mat1, d_mat + (static_cast<size_t>(layer) * 2) * mw, mw * 4);
+    e.dev().d2h(mat2, d_mat + (static_cast<size_t>(layer) * 2 + 1) * mw, mw * 4);
+    e.dev().d2h(rc, d_mat + kMatWords + layer * 2 * kPastaT, 2 * kPastaT * 4);
+    e.dev().sync();
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Engine: device-resident BFV evaluator for the PASTA-3 transciphering + encrypted-FC path.
+// All pointer arguments of the batched methods are DEVICE pointers; `items` ciphertexts are laid out back to back
+// in SEAL's layout. Work is enqueued on the context's stream; nothing here synchronises with the host.
+#pragma once
+#include <map>
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "devconsts.h"
+#include "kernels.h"
+#include "launch.h"
+#include "params.h"
+
+namespace hhe {
+
+class Engine {
+ public:
+  Engine(const Params &p, int device, void *stream);
+  ~Engine();
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+
+  const Params &params() const { return P_; }
+  Device &dev() { return dev_; }
+  size_t ct_words(int size = 2) const { return static_cast<size_t>(size) * P_.L * P_.N; }
+  int batch_limit() const { return batch_; }
+  void set_batch(int b) { batch_ = b; }
+
+  // ---- scratch arena (stack discipline, stream ordered) ----
+  struct Scope {
+    Engine &e;
+    size_t chunk, used;
+    explicit Scope(Engine &eng) : e(eng), chunk(eng.cur_chunk_), used(eng.chunks_.empty() ? 0 : eng.chunks_[eng.cur_chunk_].used) {}
+    ~Scope() { e.arena_restore(chunk, used); }
+  };
+  u64 *scratch(size_t words);
+
+  // ---- keys ----
+  void load_ksk(int kind, u32 elt, const u64 *host_ksk);
+  const W2 *find_key(int kind, u32 elt) const;
+
+  // ---- primitives (device pointers) ----
+  void ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse);
+  void add(const u64 *a, const u64 *b, u64 *out, size_t items, int size = 2);
+  void negate(const u64 *a, u64 *out, size_t items);
+  void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first);
+  void broadcast(const u64 *src, u64 *out, size_t words, size_t items);
+  void encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items);
+  void encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items);
+  void lift_ntt(const u64 *pt, u64 *D, size_t items);
+  void ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first);
+  void ct_intt(u64 *ct, size_t items, int size = 2);
+  void multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items);
+  void galois(const u64 *a, u32 elt, u64 *out, size_t items);
+  // out[c] = ModDown(sum_J NTT(target_J) * key) + base_c ; target/base given with item strides (words)
+  void key_switch(const u64 *target, size_t tstride, const W2 *key, const u64 *base0, const u64 *base1, size_t bstride,
+                  u64 *out, size_t items);
+  void apply_galois(const u64 *a, u32 elt, const W2 *key, u64 *out, size_t items);
+  void rotate_rows(const u64 *a, int steps, int keyset, u64 *out, size_t items);
+  void rotate_columns(const u64 *a, int keyset, u64 *out, size_t items);
+  void relinearize(const u64 *a3, u64 *out, size_t items);
+  void multiply(const u64 *a, const u64 *b, u64 *out3, size_t items);
+  void exponentiate3(const u64 *a, u64 *out, size_t items);
+
+  // ---- hot path ----
+  void material(const u64 *d_counters, size_t nblocks, u64 nonce, u32 *d_out);
+  void pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const std::vector<u64> &counters,
+                       u64 nonce, bool use_bsgs, u64 *d_out);
+  void mask(const u64 *a, const u64 *d_mask_slots, u32 n, u64 *out, size_t items);
+  void flatten(const u64 *in, size_t per, int keyset, u64 *out, size_t items);
+  void vec_sum(const u64 *a, size_t n, int keyset, u64 *out, size_t items);
+
+  const DevConsts *dconsts() const { return dC_; }
+  TwRef twref() const { return TwRef{dTw_, P_.N}; }
+  const u32 *index_map() const { return dIndex_; }
+
+ private:
+  friend struct Scope;
+  void arena_restore(size_t chunk, size_t used);
+  void pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb, u64 nonce,
+                   bool use_bsgs, u64 *d_out);
+  void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb);
+  void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb);
+  void feistel(u64 *state, size_t nb);
+  const W2 *need_key(int kind, u32 elt) const;
+  const u64 *feistel_mask_ntt();
+
+  Params P_;
+  Device dev_;
+  int device_ = 0;
+  int batch_ = 0;
+  DevConsts *dC_ = nullptr;
+  W2 *dTw_ = nullptr;
+  u32 *dIndex_ = nullptr;
+  u64 *dFeistel_ = nullptr;  // cached NTT of the lifted Feistel mask, [L][N]
+  std::map<std::pair<int, u32>, W2 *> keys_;
+  struct Chunk {
+    u64 *ptr;
+    size_t words, used;
+  };
+  std::vector<Chunk> chunks_;
+  size_t cur_chunk_ = 0;
+};
+
+}  // namespace hhe

@@ -1,0 +1,38 @@
+// Host/device glue. Kernel bodies are written once as functors whose operator() is structured in
+// barrier-separated phases: FOR_THREADS(tid) { ... } SYNC(); No per-thread state crosses a SYNC() -- everything a
+// later phase needs lives in shared or global memory. Under nvcc a body runs as one CUDA thread of a CTA; when the
+// same header is compiled by g++ with -DHHE_EMULATE (tests/emul only, never shipped, never loaded by the package)
+// FOR_THREADS becomes a sequential loop over the CTA's threads so the index arithmetic of every kernel can be unit
+// tested on a machine without a GPU. The emulation build is a test harness for host logic, not a CPU fallback.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__) && !defined(HHE_EMULATE)
+#define HHE_CUDA 1
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+#else
+#define HD inline
+#define DEV inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define FOR_THREADS(tid, nt) for (int tid = threadIdx.x, hhe_once_ = 1; hhe_once_; hhe_once_ = 0)
+#define SYNC() __syncthreads()
+#else
+#define FOR_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
+#define SYNC() ((void)0)
+#endif
+
+namespace hhe {
+using u32 = uint32_t;
+using u64 = uint64_t;
+
+HD u64 mulhi64(u64 a, u64 b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return static_cast<u64>((static_cast<unsigned __int128>(a) * b) >> 64);
+#endif
+}
+}  // namespace hhe

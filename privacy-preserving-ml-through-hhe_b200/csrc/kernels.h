@@ -1,0 +1,560 @@
+// Kernel bodies (functors, host+device). Each is launched through launch.h as one CUDA kernel on sm_100a.
+// Layouts: ciphertext batch u64[count][size][L][N]; key-switch accumulators u64[count][2][K][N];
+// key-switching keys W2[L][2][K][N] (value + Shoup quotient, NTT form); twiddles W2[table][fwd|inv][N].
+#pragma once
+#include "devconsts.h"
+#include "ntt_core.h"
+
+namespace hhe {
+
+struct TwRef {
+  const W2 *base;  // all tables
+  u64 N;
+  HD const W2 *fwd(int tab) const { return base + (static_cast<size_t>(tab) * 2) * N; }
+  HD const W2 *inv(int tab) const { return base + (static_cast<size_t>(tab) * 2 + 1) * N; }
+};
+
+struct TabMap {  // limb index inside an item -> NTT table id
+  unsigned char id[kMaxTab];
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Plain batched NTT / inverse NTT of whole limbs: grid = count * limbs, CTA = one limb in shared memory.
+// Replaces seal::util::ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (seal/util/ntt.h:195-340).
+template <int LOGS>
+struct NttBody {
+  const u64 *in;
+  u64 *out;
+  const DevConsts *C;
+  TwRef tw;
+  TabMap map;
+  int limbs;
+  int inverse;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    const int tab = map.id[bid % limbs];
+    const u64 q = C->mod[tab].q;
+    const u64 *src = in + static_cast<size_t>(bid) * S;
+    u64 *dst = out + static_cast<size_t>(bid) * S;
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) sm[pidx(i)] = src[i];
+    }
+    SYNC();
+    if (!inverse) {
+      ntt_fwd_core<LOGS>(sm, tw.fwd(tab), q, 1, nt);
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) dst[i] = csub(csub(sm[pidx(i)], q << 1), q);
+      }
+    } else {
+      ntt_inv_core<LOGS>(sm, tw.inv(tab), q, 1, nt);
+      const W2 ninv = C->n_inv[tab];
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) dst[i] = mul_shoup(sm[pidx(i)], ninv, q);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Key-switch digit kernel (Evaluator::switch_key_inplace inner loops, seal/evaluator.h:1260):
+//   acc[b][c][k] = sum_J NTT_k( target[b][J] mod q_k ) (.) key[J][c][k]
+// One CTA per (b, key limb k, half h): the first Cooley-Tukey stage is folded into the load so each CTA owns an
+// independent N/2-point sub-transform (64 KiB at N=16384) and keeps both components' accumulators for its half in
+// shared memory (128 KiB) across the digit loop -- the accumulators never touch HBM until the inner product is done.
+// Grid order puts b fastest so co-resident CTAs read the same key tile from L2.
+template <int LOGH>
+struct KsDigitsBody {
+  const u64 *target;  // [count][..] : item b's target polynomial (L limbs) at target + b*stride
+  size_t stride;
+  const W2 *key;  // [L][2][K][N]
+  u64 *acc;       // [count][2][K][N], NTT form, canonical
+  const DevConsts *C;
+  TwRef tw;
+  int count;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH;
+    const int N = 2 * S;
+    const int K = C->K, L = C->L;
+    const int b = bid % count;
+    const int kh = bid / count;
+    const int k = kh >> 1, h = kh & 1;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    u64 *acc0 = sm + ntt_smem_words(S);
+    u64 *acc1 = acc0 + S;
+    const DevMod mk = C->mod[k];
+    const u64 q = mk.q, two_q = q << 1;
+    const W2 *twk = tw.fwd(k);
+    const W2 w1 = twk[1];
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) acc0[i] = acc1[i] = 0;
+    }
+    for (int J = 0; J < L; ++J) {
+      const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
+      const bool reduce = C->mod[J].q > q;
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) {
+          u64 x = dig[i], y = dig[i + S];
+          if (reduce) {
+            x = barrett64(x, mk);
+            y = barrett64(y, mk);
+          }
+          const u64 t = mul_shoup_lazy(y, w1.w, w1.ws, q);
+          sm[pidx(i)] = h ? x + two_q - t : x + t;
+        }
+      }
+      SYNC();
+      ntt_fwd_core<LOGH>(sm, twk, q, 2 + h, nt);
+      const W2 *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+      const W2 *k1 = k0 + static_cast<size_t>(K) * N;
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) {
+          const u64 v = sm[pidx(i)];
+          const W2 a = k0[i], c = k1[i];
+          u64 s0 = acc0[i] + mul_shoup_lazy(v, a.w, a.ws, q);
+          u64 s1 = acc1[i] + mul_shoup_lazy(v, c.w, c.ws, q);
+          acc0[i] = s0 >= two_q ? s0 - two_q : s0;
+          acc1[i] = s1 >= two_q ? s1 - two_q : s1;
+        }
+      }
+      SYNC();
+    }
+    u64 *o0 = acc + ((static_cast<size_t>(b) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+    u64 *o1 = o0 + static_cast<size_t>(K) * N;
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) {
+        o0[i] = csub(acc0[i], q);
+        o1[i] = csub(acc1[i], q);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// ModDown with rounding (second half of switch_key_inplace) fused with the final additions:
+//   out[c][i] = ( acc[c][i] - (r_c mod q_i) + (half mod q_i) ) * q_sp^-1  +  base_c[i],  r_c = acc[c][sp] + half mod q_sp
+// acc is in coefficient form (after the inverse NTT). base1 may be NULL (rotations: component 1 starts from zero).
+struct ModDownBody {
+  const u64 *acc;    // [count][2][K][N]
+  const u64 *base0;  // item b at base0 + b*bstride : [L][N]
+  const u64 *base1;
+  size_t bstride;
+  u64 *out;  // [count][2][L][N]
+  const DevConsts *C;
+  size_t total;  // count * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const int K = C->K, L = C->L;
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t b = g / N, j = g % N;
+        const DevMod msp = C->mod[K - 1];
+        for (int c = 0; c < 2; ++c) {
+          const u64 *a = acc + ((b * 2 + c) * K) * N + j;
+          u64 r = a[static_cast<size_t>(K - 1) * N] + C->half_sp;
+          r = csub(r, msp.q);
+          const u64 *base = c ? base1 : base0;
+          for (int i = 0; i < L; ++i) {
+            const DevMod mi = C->mod[i];
+            u64 ri = msp.q > mi.q ? barrett64(r, mi) : r;
+            u64 v = sub_mod(a[static_cast<size_t>(i) * N], ri, mi.q);
+            v = add_mod(v, C->half_sp_mod_q[i], mi.q);
+            v = mul_shoup(v, C->inv_sp_mod_q[i], mi.q);
+            if (base) v = add_mod(v, base[b * bstride + static_cast<size_t>(i) * N + j], mi.q);
+            out[((b * 2 + c) * L + i) * N + j] = v;
+          }
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// GaloisTool::apply_galois on coefficient-form ciphertexts (seal/util/galois.h:32-33), gather form:
+//   out[idx] = +-in[i],  i*elt = idx or idx+N (mod 2N)  <=>  i' = idx*elt^-1 mod 2N, i = i' mod N, sign = i' >= N
+struct GaloisBody {
+  const u64 *in;  // [count][2][L][N]
+  u64 *out;
+  const DevConsts *C;
+  u32 elt_inv;
+  size_t total;  // count*2*L*N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t limb = g / N, idx = g % N;
+        const u64 q = C->mod[limb % C->L].q;
+        const u64 ip = (idx * elt_inv) & (2 * N - 1);
+        u64 v = in[limb * N + (ip & (N - 1))];
+        if (ip >= N) v = neg_mod(v, q);
+        out[g] = v;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Element-wise ciphertext ops (Evaluator::add / negate / add_plain, seal/evaluator.h:92,118,665)
+struct AddBody {  // out = a + b (optionally a + b where b has item stride 0)
+  const u64 *a, *b;
+  u64 *out;
+  const DevConsts *C;
+  int limbs;  // limbs per item (size * L)
+  size_t total;
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const u64 q = C->mod[(g / N) % limbs % C->L].q;
+        out[g] = add_mod(a[g], b[g], q);
+      }
+    }
+  }
+};
+
+struct NegateBody {
+  const u64 *a;
+  u64 *out;
+  const DevConsts *C;
+  size_t total;
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) out[g] = neg_mod(a[g], C->mod[(g / N) % C->L].q);
+    }
+  }
+};
+
+// out = (negate ? -a : a) + Delta-scaled plaintext on component 0 (multiply_add_plain_with_scaling_variant):
+//   c0[j] += m_j*floor(Q/t) + floor((m_j*(Q mod t) + (t+1)/2) / t)
+struct AddPlainBody {
+  const u64 *a;   // [count][2][L][N]
+  const u64 *pt;  // [count][N], item stride pstride (0 = shared)
+  size_t pstride;
+  u64 *out;
+  const DevConsts *C;
+  int negate;
+  size_t total;  // count*2*L*N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    const int L = C->L;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t limb = g / N, j = g % N;
+        const int i = static_cast<int>(limb % L);
+        const size_t item = limb / (2 * L);
+        const int comp = static_cast<int>((limb / L) & 1);
+        const DevMod mi = C->mod[i];
+        u64 v = a[g];
+        if (negate) v = neg_mod(v, mi.q);
+        if (comp == 0) {
+          const u64 m = pt[item * pstride + j];
+          const u64 fix = (m * C->q_mod_t + C->half_t) / C->t;  // m, Q mod t < 2^32
+          v = add_mod(v, mul_add_mod(m, C->q_div_t_mod_q[i], fix, mi), mi.q);
+        }
+        out[g] = v;
+      }
+    }
+  }
+};
+
+struct BroadcastBody {  // out[item] = src for every item
+  const u64 *src;
+  u64 *out;
+  size_t words, total;
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) out[g] = src[g % words];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// BatchEncoder::encode (seal/batchencoder.h:80): scatter slot values through the index map, inverse NTT mod t.
+// One CTA per plaintext. The slot source depends on `mode`:
+//   kSlots     : u64 slots[item][sstride], first lens[item] (or n) valid          (mask, symmetric ciphertext block)
+//   kDiag      : PASTA diagonal `diag` of layer `layer` from the generated matrices (pasta_3_seal.cpp:388-401)
+//   kDiagBsgs  : same, pre-rotated for baby-step/giant-step                         (pasta_3_seal.cpp:281-326)
+//   kRc        : round constants of layer `layer`                                   (pasta_3_plain.cpp:286-295)
+//   kFeistel   : the constant Feistel mask                                          (pasta_3_seal.cpp:229-235)
+enum EncodeMode { kSlots = 0, kDiag = 1, kDiagBsgs = 2, kRc = 3, kFeistel = 4 };
+
+// material layout per block: u32 [4 layers][2 matrices][128][128], then u32 rc[4][256]
+constexpr size_t kMatWords = static_cast<size_t>(4) * 2 * kPastaT * kPastaT;
+constexpr size_t kMaterialWords = kMatWords + 4 * 2 * kPastaT;
+
+template <int LOGS>
+struct EncodeBody {
+  const u64 *slots;
+  size_t sstride;
+  const u32 *lens;  // per item valid count (NULL: n)
+  u32 n;
+  const u32 *material;  // [items][kMaterialWords]
+  const u32 *mat_index; // item -> material row (NULL: identity)
+  const u32 *index_map;
+  u64 *pt;  // [items][N]
+  const DevConsts *C;
+  TwRef tw;
+  int mode, layer, diag;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    constexpr int T = kPastaT;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    const int tab = 2 * C->K;
+    const u64 t = C->t;
+    const int half = S / 2;
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) sm[pidx(i)] = 0;
+    }
+    SYNC();
+    const u32 *mat = material ? material + static_cast<size_t>(mat_index ? mat_index[bid] : bid) * kMaterialWords : nullptr;
+    FOR_THREADS(tid, nt) {
+      if (mode == kSlots) {
+        const u32 cnt = lens ? lens[bid] : n;
+        for (u32 i = tid; i < cnt; i += nt) sm[pidx(index_map[i])] = slots[static_cast<size_t>(bid) * sstride + i];
+      } else if (mode == kRc) {
+        for (int i = tid; i < 2 * T; i += nt) {
+          const int slot = i < T ? i : half + (i - T);
+          sm[pidx(index_map[slot])] = mat[kMatWords + layer * 2 * T + i];
+        }
+      } else if (mode == kFeistel) {
+        for (int i = tid; i < 2 * T; i += nt) {
+          const int j = i & (T - 1);
+          if (j) sm[pidx(index_map[(i < T ? 0 : half) + j])] = 1;
+        }
+      } else {
+        // diagonal `diag`: entry j of matrix M is M[j][(j - diag) mod T]
+        for (int i = tid; i < 2 * T; i += nt) {
+          const int which = i >= T, p = i & (T - 1);
+          const u32 *M = mat + (static_cast<size_t>(layer) * 2 + which) * T * T;
+          int slot = p, src = p;
+          if (mode == kDiagBsgs) {
+            const int shift = (diag / 16) * 16;  // giant-step pre-rotation k*N1
+            src = (p + shift) & (T - 1);
+            if (half != T && p >= T - shift) slot = p + (half - T);
+          }
+          const u32 v = M[src * T + ((src + T - diag) & (T - 1))];
+          sm[pidx(index_map[which * half + slot])] = v;
+        }
+      }
+    }
+    SYNC();
+    ntt_inv_core<LOGS>(sm, tw.inv(tab), t, 1, nt);
+    const W2 ninv = C->n_inv[tab];
+    u64 *dst = pt + static_cast<size_t>(bid) * S;
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) dst[i] = mul_shoup(sm[pidx(i)], ninv, t);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Plaintext half of Evaluator::multiply_plain (seal/evaluator.h:729): centred lift of pt into limb i, forward NTT.
+// grid = items * L
+template <int LOGS>
+struct LiftNttBody {
+  const u64 *pt;  // [items][N]
+  u64 *out;       // [items][L][N]
+  const DevConsts *C;
+  TwRef tw;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    const int L = C->L, i = bid % L;
+    const size_t item = bid / L;
+    const u64 q = C->mod[i].q, inc = q - C->t, thr = C->half_t;
+    const u64 *src = pt + item * S;
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) {
+        const u64 m = src[j];
+        sm[pidx(j)] = m >= thr ? m + inc : m;
+      }
+    }
+    SYNC();
+    ntt_fwd_core<LOGS>(sm, tw.fwd(i), q, 1, nt);
+    u64 *dst = out + static_cast<size_t>(bid) * S;
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) dst[j] = csub(csub(sm[pidx(j)], q << 1), q);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Ciphertext half of multiply_plain, accumulated in the NTT domain:
+//   sum[b][c][i] (+)= NTT_i(ct[b][c][i]) (.) D[b][i]          grid = items * 2 * L
+// (the PASTA diagonal loop sums 128 such products; accumulation before the single inverse NTT is exact)
+template <int LOGS>
+struct NttMacBody {
+  const u64 *ct;  // [items][2][L][N] coefficient form
+  const u64 *D;   // [items][L][N] (dstride = L*N) or shared (dstride = 0)
+  size_t dstride;
+  u64 *sum;
+  const DevConsts *C;
+  TwRef tw;
+  int first;  // 1: overwrite
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    const int L = C->L, i = bid % L;
+    const size_t item = bid / (2 * L);
+    const DevMod mi = C->mod[i];
+    const u64 q = mi.q;
+    const u64 *src = ct + static_cast<size_t>(bid) * S;
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) sm[pidx(j)] = src[j];
+    }
+    SYNC();
+    ntt_fwd_core<LOGS>(sm, tw.fwd(i), q, 1, nt);
+    const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
+    u64 *dst = sum + static_cast<size_t>(bid) * S;
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) {
+        u64 v = mul_mod(sm[pidx(j)], d[j], mi);
+        if (!first) v = add_mod(v, dst[j], q);
+        dst[j] = v;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// BEHZ multiplication (Evaluator::bfv_multiply, seal/evaluator.h:214; RNSTool, seal/util/rns.h:213-228)
+
+// fastbconv_m_tilde + sm_mrq: x (base q, coefficient form) -> x in base Bsk.  One thread per (poly, coefficient).
+struct BehzExtendBody {
+  const u64 *x;  // [polys][L][N]
+  u64 *xb;       // [polys][L+1][N]
+  const DevConsts *C;
+  size_t total;  // polys * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const int L = C->L;
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t p = g / N, j = g % N;
+        u64 z[kMaxLimbs];
+        u32 mt = 0;
+        for (int i = 0; i < L; ++i) {
+          z[i] = mul_shoup(x[(p * L + i) * N + j], C->mtilde_ipq[i], C->mod[i].q);
+          mt += static_cast<u32>(z[i]) * C->q2mt[i];
+        }
+        const u32 r = mt * C->neg_inv_q_mt;
+        for (int bb = 0; bb <= L; ++bb) {
+          const DevMod mb = C->mod[C->K + bb];
+          u64 s = 0;
+          for (int i = 0; i < L; ++i) s = mul_add_mod(z[i], C->q2bsk[bb][i], s, mb);
+          const u64 rp = r >= 0x80000000u ? mb.q - (0x100000000ULL - r) : r;
+          const u64 v = mul_add_mod(rp, C->q_mod_bsk[bb], s, mb);
+          xb[(p * (L + 1) + bb) * N + j] = mul_shoup(v, C->inv_mt_bsk[bb], mb.q);
+        }
+      }
+    }
+  }
+};
+
+// NTT-domain tensor product for one base: d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1.
+// a, b: [items][2][limbs][N]; d: [items][3][limbs][N]; table id of limb l is tab0 + l.
+struct TensorBody {
+  const u64 *a, *b;
+  u64 *d;
+  const DevConsts *C;
+  int limbs, tab0;
+  size_t total;  // items * limbs * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t j = g % N, l = (g / N) % limbs, item = g / (N * limbs);
+        const DevMod m = C->mod[tab0 + l];
+        const size_t poly = static_cast<size_t>(limbs) * N, off = l * N + j;
+        const u64 a0 = a[item * 2 * poly + off], a1 = a[item * 2 * poly + poly + off];
+        const u64 b0 = b[item * 2 * poly + off], b1 = b[item * 2 * poly + poly + off];
+        u64 *o = d + item * 3 * poly + off;
+        o[0] = mul_mod(a0, b0, m);
+        o[poly] = add_mod(mul_mod(a0, b1, m), mul_mod(a1, b0, m), m.q);
+        o[2 * poly] = mul_mod(a1, b1, m);
+      }
+    }
+  }
+};
+
+// multiply by t, fast_floor, fastbconv_sk: (d in base q, d in base Bsk; coefficient form) -> round(t*d/Q) in base q
+struct BehzScaleRoundBody {
+  const u64 *dq;  // [polys][L][N]
+  const u64 *db;  // [polys][L+1][N]
+  u64 *out;       // [polys][L][N]
+  const DevConsts *C;
+  size_t total;  // polys * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const int L = C->L, K = C->K;
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t p = g / N, j = g % N;
+        u64 z[kMaxLimbs], f[kMaxLimbs];
+        for (int i = 0; i < L; ++i) z[i] = mul_shoup(dq[(p * L + i) * N + j], C->t_ipq[i], C->mod[i].q);
+        for (int bb = 0; bb <= L; ++bb) {
+          const DevMod mb = C->mod[K + bb];
+          u64 s = 0;
+          for (int i = 0; i < L; ++i) s = mul_add_mod(z[i], C->q2bsk[bb][i], s, mb);
+          const u64 tb = mul_shoup(db[(p * (L + 1) + bb) * N + j], C->t_mod_bsk[bb], mb.q);
+          f[bb] = mul_shoup(sub_mod(tb, s, mb.q), C->inv_q_bsk[bb], mb.q);
+        }
+        const u64 f_sk = f[L];
+        const DevMod msk = C->mod[K + L];
+        u64 sk = 0;
+        for (int i = 0; i < L; ++i) {
+          f[i] = mul_shoup(f[i], C->inv_punct_b[i], C->mod[K + i].q);
+          sk = mul_add_mod(f[i], C->b2msk[i], sk, msk);
+        }
+        const u64 alpha = mul_shoup(sub_mod(sk, f_sk, msk.q), C->inv_pb_msk, msk.q);
+        const bool upper = alpha > (msk.q >> 1);
+        for (int jq = 0; jq < L; ++jq) {
+          const DevMod mq = C->mod[jq];
+          u64 s = 0;
+          for (int i = 0; i < L; ++i) s = mul_add_mod(f[i], C->b2q[jq][i], s, mq);
+          s = upper ? mul_add_mod(msk.q - alpha, C->pb_mod_q[jq], s, mq) : mul_add_mod(alpha, mq.q - C->pb_mod_q[jq], s, mq);
+          out[(p * L + jq) * N + j] = s;
+        }
+      }
+    }
+  }
+};
+
+// value -> (value, floor(value * 2^64 / q)) for uploaded key-switching keys (one-time, at hhe_load_ksk)
+struct ShoupifyBody {
+  const u64 *in;  // [L][2][K][N]
+  W2 *out;
+  const DevConsts *C;
+  size_t total;
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const DevMod m = C->mod[(g / N) % C->K];
+        const u64 w = in[g];
+        // floor(w * 2^64 / q): Barrett estimate from floor(2^128/q), then exact correction
+        u64 est = mulhi64(w, m.cr0) + w * m.cr1;
+        // remainder check: w*2^64 - est*q must be in [0, q)
+        u64 rem = 0 - est * m.q;  // low 64 bits of (w<<64) - est*q
+        while (rem >= m.q) {
+          rem -= m.q;
+          ++est;
+        }
+        out[g] = W2{w, est};
+      }
+    }
+  }
+};
+
+}  // namespace hhe

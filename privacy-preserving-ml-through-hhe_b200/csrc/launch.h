@@ -1,0 +1,115 @@
+// Device runtime shim: memory, copies, stream sync and kernel launch.
+// CUDA build (nvcc, sm_100a): the real thing. -DHHE_EMULATE (g++, tests/emul only): the grid is walked on the host
+// so host-side orchestration and kernel index arithmetic can be unit-tested without a GPU. The emulation object is
+// never part of libhhe_b200.so and the Python package never loads it.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hd.h"
+
+#ifdef HHE_CUDA
+#include <cuda_runtime.h>
+#endif
+
+namespace hhe {
+
+#ifdef HHE_CUDA
+inline void cuda_check(cudaError_t e, const char *what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+template <class Body>
+__global__ void __launch_bounds__(512) kernel_entry(const Body body) {
+  extern __shared__ __align__(16) unsigned char hhe_smem[];
+  body(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
+}
+#endif
+
+struct Device {
+#ifdef HHE_CUDA
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+#endif
+  int sm_count = 1;
+  uint64_t launches = 0;
+
+  void *dmalloc(size_t bytes) {
+#ifdef HHE_CUDA
+    void *p = nullptr;
+    cuda_check(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
+    return p;
+#else
+    void *p = std::malloc(bytes ? bytes : 1);
+    if (!p) throw std::runtime_error("malloc failed");
+    return p;
+#endif
+  }
+  void dfree(void *p) {
+#ifdef HHE_CUDA
+    if (p) cudaFree(p);
+#else
+    std::free(p);
+#endif
+  }
+  void h2d(void *dst, const void *src, size_t bytes) {
+#ifdef HHE_CUDA
+    cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream), "cudaMemcpyAsync H2D");
+#else
+    std::memcpy(dst, src, bytes);
+#endif
+  }
+  void d2h(void *dst, const void *src, size_t bytes) {
+#ifdef HHE_CUDA
+    cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream), "cudaMemcpyAsync D2H");
+#else
+    std::memcpy(dst, src, bytes);
+#endif
+  }
+  void d2d(void *dst, const void *src, size_t bytes) {
+#ifdef HHE_CUDA
+    cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync D2D");
+#else
+    std::memmove(dst, src, bytes);
+#endif
+  }
+  void zero(void *dst, size_t bytes) {
+#ifdef HHE_CUDA
+    cuda_check(cudaMemsetAsync(dst, 0, bytes, stream), "cudaMemsetAsync");
+#else
+    std::memset(dst, 0, bytes);
+#endif
+  }
+  void sync() {
+#ifdef HHE_CUDA
+    cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+#endif
+  }
+
+  template <class Body>
+  void launch(const Body &body, size_t grid, int nt, size_t smem_bytes) {
+    if (grid == 0) return;
+    ++launches;
+#ifdef HHE_CUDA
+    if (smem_bytes > 48 * 1024) {
+      static size_t configured = 0;  // per Body instantiation
+      if (smem_bytes > configured) {
+        cuda_check(cudaFuncSetAttribute(kernel_entry<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem_bytes)),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        configured = smem_bytes;
+      }
+    }
+    kernel_entry<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
+    cuda_check(cudaGetLastError(), "kernel launch");
+#else
+    std::vector<unsigned char> smem(smem_bytes + 16);
+    for (size_t b = 0; b < grid; ++b) body(static_cast<int>(b), nt, smem.data());
+#endif
+  }
+};
+
+}  // namespace hhe

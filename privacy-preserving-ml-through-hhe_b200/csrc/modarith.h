@@ -1,0 +1,67 @@
+// 64-bit modular arithmetic primitives (host+device). Moduli are < 2^61.
+//   Shoup multiplication by a constant with precomputed quotient (seal/util/uintarithsmallmod.h:255-326)
+//   Barrett 128->64 and 64->64 reduction (seal/util/uintarithsmallmod.h:167-230)
+// Only the mathematical residue matters for parity: every value that leaves a kernel is canonical in [0, q).
+#pragma once
+#include "hd.h"
+
+namespace hhe {
+
+struct Twiddle;  // params.h; layout {w, ws}
+
+struct DevMod {
+  u64 q;
+  u64 cr0, cr1;  // floor(2^128 / q), low and high words
+};
+
+struct W2 {  // device view of a Shoup pair
+  u64 w, ws;
+};
+
+// x * w mod q, result in [0, 2q), any 64-bit x
+HD u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 q) { return x * w - mulhi64(x, ws) * q; }
+HD u64 mul_shoup(u64 x, u64 w, u64 ws, u64 q) {
+  u64 r = mul_shoup_lazy(x, w, ws, q);
+  return r >= q ? r - q : r;
+}
+HD u64 mul_shoup(u64 x, W2 c, u64 q) { return mul_shoup(x, c.w, c.ws, q); }
+
+HD u64 add_mod(u64 a, u64 b, u64 q) {
+  u64 s = a + b;
+  return s >= q ? s - q : s;
+}
+HD u64 sub_mod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+HD u64 neg_mod(u64 a, u64 q) { return a ? q - a : 0; }
+HD u64 csub(u64 a, u64 q) { return a >= q ? a - q : a; }
+
+// x mod q for any 64-bit x
+HD u64 barrett64(u64 x, const DevMod &m) {
+  u64 r = x - mulhi64(x, m.cr1) * m.q;
+  return r >= m.q ? r - m.q : r;
+}
+
+// (hi:lo) mod q, requires the result of the estimate to fit, i.e. hi < q (always true for products of residues)
+HD u64 barrett128(u64 lo, u64 hi, const DevMod &m) {
+  // qhat = floor((hi:lo) * (cr1:cr0) / 2^128), assembled from 64-bit partial products
+  u64 c = mulhi64(lo, m.cr0);
+  u64 p1l = lo * m.cr1, p1h = mulhi64(lo, m.cr1);
+  u64 s1 = p1l + c;
+  u64 k1 = p1h + (s1 < p1l);
+  u64 p2l = hi * m.cr0, p2h = mulhi64(hi, m.cr0);
+  u64 s2 = s1 + p2l;
+  u64 k2 = p2h + (s2 < s1);
+  u64 qhat = hi * m.cr1 + k1 + k2;
+  u64 r = lo - qhat * m.q;
+  return r >= m.q ? r - m.q : r;
+}
+
+HD u64 mul_mod(u64 a, u64 b, const DevMod &m) { return barrett128(a * b, mulhi64(a, b), m); }
+// a*b + c mod q  (c < 2^64, a*b + c must stay below q * 2^64)
+HD u64 mul_add_mod(u64 a, u64 b, u64 c, const DevMod &m) {
+  u64 lo = a * b, hi = mulhi64(a, b);
+  lo += c;
+  hi += (lo < c);
+  return barrett128(lo, hi, m);
+}
+
+}  // namespace hhe

@@ -1,0 +1,123 @@
+// Shared-memory negacyclic NTT core (host+device). One CTA owns one (sub-)transform of S = 2^LOGS residues staged
+// in shared memory; each thread runs radix-16 (four radix-2 stages) butterflies in registers between barriers, so a
+// 2^14 transform needs 4 passes over shared memory instead of 14.
+//
+// Semantics follow SEAL's transform (seal/util/dwthandler.h:94-356, seal/util/ntt.h): forward = Cooley-Tukey,
+// natural-order input, bit-reversed output, stage with m groups uses twiddles fwd[m + i] = psi^bitrev(m+i);
+// inverse = Gentleman-Sande with inv[m + i] on the same (m, i) pairing. Harvey lazy butterflies: forward values
+// stay in [0, 4q), inverse values in [0, 2q); callers canonicalise on the way out.
+//
+// A transform of size S may be a *sub-transform* of a larger N-point one: after the first log2(N/S) Cooley-Tukey
+// stages the N/S contiguous chunks are independent; `mc` = (N/S) + chunk selects the twiddle rows of that chunk.
+#pragma once
+#include "modarith.h"
+
+namespace hhe {
+
+// Shared-memory index padding: one extra word per 16 keeps the stride-16/stride-1 mixes of the register passes
+// spread over the banks.
+HD int pidx(int i) { return i + (i >> 4); }
+constexpr size_t ntt_smem_words(int S) { return static_cast<size_t>(S) + (S >> 4); }
+
+HD void fwd_bfly(u64 &a, u64 &b, W2 w, u64 q, u64 two_q) {
+  u64 x = a >= two_q ? a - two_q : a;
+  u64 t = mul_shoup_lazy(b, w.w, w.ws, q);
+  a = x + t;
+  b = x + two_q - t;
+}
+HD void inv_bfly(u64 &a, u64 &b, W2 w, u64 q, u64 two_q) {
+  u64 s = a + b;
+  u64 d = a + two_q - b;
+  a = s >= two_q ? s - two_q : s;
+  b = mul_shoup_lazy(d, w.w, w.ws, q);
+}
+
+// One register pass over stages [s0, s0+R) for group g (2^R residues).
+template <int R>
+HD void fwd_group(u64 *sm, const W2 *__restrict__ tw, u64 q, int logS, int s0, u32 mc, int g) {
+  constexpr int E = 1 << R;
+  const int lg = logS - s0 - R;
+  const int lo = g & ((1 << lg) - 1), hi = g >> lg;
+  const int base = (hi << (logS - s0)) + lo;
+  const u64 two_q = q << 1;
+  u64 x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = sm[pidx(base + (e << lg))];
+#pragma unroll
+  for (int d = 0; d < R; ++d) {
+    const int half = E >> (d + 1);
+    const u32 tb = (mc << (s0 + d)) + (static_cast<u32>(hi) << d);
+#pragma unroll
+    for (int j = 0; j < (1 << d); ++j) {
+      const W2 w = tw[tb + j];
+#pragma unroll
+      for (int k = 0; k < half; ++k) fwd_bfly(x[2 * j * half + k], x[2 * j * half + k + half], w, q, two_q);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) sm[pidx(base + (e << lg))] = x[e];
+}
+
+template <int R>
+HD void inv_group(u64 *sm, const W2 *__restrict__ tw, u64 q, int logS, int s0, u32 mc, int g) {
+  constexpr int E = 1 << R;
+  const int lg = logS - s0 - R;
+  const int lo = g & ((1 << lg) - 1), hi = g >> lg;
+  const int base = (hi << (logS - s0)) + lo;
+  const u64 two_q = q << 1;
+  u64 x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = sm[pidx(base + (e << lg))];
+#pragma unroll
+  for (int d = R - 1; d >= 0; --d) {
+    const int half = E >> (d + 1);
+    const u32 tb = (mc << (s0 + d)) + (static_cast<u32>(hi) << d);
+#pragma unroll
+    for (int j = 0; j < (1 << d); ++j) {
+      const W2 w = tw[tb + j];
+#pragma unroll
+      for (int k = 0; k < half; ++k) inv_bfly(x[2 * j * half + k], x[2 * j * half + k + half], w, q, two_q);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) sm[pidx(base + (e << lg))] = x[e];
+}
+
+template <int LOGS>
+struct NttSchedule {
+  static constexpr int kFirst = LOGS - 4 * ((LOGS - 1) / 4);  // 1..4 stages in the odd-sized pass
+};
+
+// Forward transform of the S residues in sm (padded layout). In: [0, 4q). Out: [0, 4q). Ends with a barrier.
+template <int LOGS>
+HD void ntt_fwd_core(u64 *sm, const W2 *__restrict__ tw, u64 q, u32 mc, int nt) {
+  constexpr int R0 = NttSchedule<LOGS>::kFirst;
+  FOR_THREADS(tid, nt) {
+    for (int g = tid; g < (1 << (LOGS - R0)); g += nt) fwd_group<R0>(sm, tw, q, LOGS, 0, mc, g);
+  }
+  SYNC();
+  for (int s0 = R0; s0 < LOGS; s0 += 4) {
+    FOR_THREADS(tid, nt) {
+      for (int g = tid; g < (1 << (LOGS - 4)); g += nt) fwd_group<4>(sm, tw, q, LOGS, s0, mc, g);
+    }
+    SYNC();
+  }
+}
+
+// Inverse transform (without the 1/N scaling). In: [0, 2q). Out: [0, 2q). Ends with a barrier.
+template <int LOGS>
+HD void ntt_inv_core(u64 *sm, const W2 *__restrict__ tw, u64 q, u32 mc, int nt) {
+  constexpr int R0 = NttSchedule<LOGS>::kFirst;
+  for (int s0 = LOGS - 4; s0 >= R0; s0 -= 4) {
+    FOR_THREADS(tid, nt) {
+      for (int g = tid; g < (1 << (LOGS - 4)); g += nt) inv_group<4>(sm, tw, q, LOGS, s0, mc, g);
+    }
+    SYNC();
+  }
+  FOR_THREADS(tid, nt) {
+    for (int g = tid; g < (1 << (LOGS - R0)); g += nt) inv_group<R0>(sm, tw, q, LOGS, 0, mc, g);
+  }
+  SYNC();
+}
+
+}  // namespace hhe

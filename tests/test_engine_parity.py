@@ -1,0 +1,276 @@
+"""Parity of the engine with the oracle and the reference's golden vectors, through the C ABI.
+
+backend "cuda" = the product (libhhe_b200.so on a B200; marked gpu).
+backend "emul" = the SAME kernel bodies and host orchestration compiled with -DHHE_EMULATE (tests/emul, a test harness
+that walks each CUDA grid on the host). It exists so that host logic and kernel index arithmetic are checked in the
+CPU-only test tier; it is not part of the package and is never used as a fallback.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+
+pkg = common.package()
+FX = np.load(os.path.join(common.ROOT, "tests", "golden", "pasta_n512.npz"))
+EMUL = os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
+BACKENDS = [pytest.param("emul"), pytest.param("cuda", marks=pytest.mark.gpu)]
+N = 1024
+BSGS_STEPS = (-16, -32, -48, -64, -80, -96, -112)
+
+
+def make_ctx(backend, NN, q):
+    if backend == "emul":
+        subprocess.check_call(["make", "-s", "-C", os.path.dirname(EMUL)])
+        return pkg.Context(NN, common.T, q, lib_path=EMUL)
+    return pkg.Context(NN, common.T, q, device=0)
+
+
+# ---- a self-contained key generator for the test ring (keys are inputs; any valid RLWE key set will do) -------------
+class ToyKeys:
+    """Secret key + key-switching keys built with the oracle's NTT (symmetric-key RLWE, SEAL's key layout)."""
+
+    def __init__(self, orc, seed):
+        self.o, self.rng = orc, np.random.default_rng(seed)
+        self.N, self.K, self.L, self.q = orc.N, orc.K, orc.L, [int(v) for v in orc.q]
+        s = self.rng.integers(-1, 2, self.N)
+        self.s_ntt = np.stack([orc.ntt(k, np.mod(s, self.q[k]).astype(np.uint64)) for k in range(self.K)])
+
+    def _mul(self, a, b, k):
+        return np.array([int(x) * int(y) % self.q[k] for x, y in zip(a, b)], dtype=np.uint64)
+
+    def ksk(self, new_key_ntt):
+        """key[J][c][k]: c0 = -(a s + e) + q_sp * new_key [only on limb J], c1 = a  (all NTT form)"""
+        out = np.zeros((self.L, 2, self.K, self.N), dtype=np.uint64)
+        qsp = self.q[-1]
+        for J in range(self.L):
+            e = self.rng.integers(-3, 4, self.N)
+            for k in range(self.K):
+                qk = self.q[k]
+                a = self.rng.integers(0, qk, self.N, dtype=np.uint64)
+                e_ntt = self.o.ntt(k, np.mod(e, qk).astype(np.uint64))
+                c0 = (qk - (self._mul(a, self.s_ntt[k], k).astype(object) + e_ntt.astype(object)) % qk) % qk
+                if k == J:
+                    c0 = (c0 + (qsp % qk) * new_key_ntt[k].astype(object)) % qk
+                out[J, 0, k] = np.array(c0, dtype=np.uint64)
+                out[J, 1, k] = a
+        return out
+
+    def galois_key(self, elt):
+        # s(X^elt) in NTT form: permute coefficient form then transform
+        s_coeff = [self.o.ntt(k, self.s_ntt[k], inverse=True) for k in range(self.K)]
+        g = np.zeros((self.K, self.N), dtype=np.uint64)
+        for k in range(self.K):
+            idx = (np.arange(self.N, dtype=np.int64) * elt) % (2 * self.N)
+            val = s_coeff[k].copy()
+            neg = idx >= self.N
+            val[neg] = (self.q[k] - val[neg]) % self.q[k]
+            tmp = np.zeros(self.N, dtype=np.uint64)
+            tmp[idx % self.N] = val
+            g[k] = self.o.ntt(k, tmp)
+        return self.ksk(g)
+
+    def relin_key(self):
+        s2 = np.stack([self._mul(self.s_ntt[k], self.s_ntt[k], k) for k in range(self.K)])
+        return self.ksk(s2)
+
+    def encrypt_zero_plus(self, orc, pt):
+        """(c0, c1) = (-(a s + e) , a) + Delta*pt on c0 -- a valid fresh BFV ciphertext of pt."""
+        ct = np.zeros((2, self.L, self.N), dtype=np.uint64)
+        e = self.rng.integers(-3, 4, self.N)
+        for i in range(self.L):
+            qi = self.q[i]
+            a = self.rng.integers(0, qi, self.N, dtype=np.uint64)
+            as_ = orc.ntt(i, self._mul(orc.ntt(i, a), self.s_ntt[i], i), inverse=True)
+            ct[0, i] = np.array((qi - (as_.astype(object) + np.mod(e, qi).astype(object)) % qi) % qi, dtype=np.uint64)
+            ct[1, i] = a
+        return orc.add_plain(ct, pt)
+
+
+@pytest.fixture(scope="module")
+def world():
+    q = common.small_params(N, 6)
+    orc = O.Oracle(N, common.T, q)
+    keys = ToyKeys(orc, 42)
+    steps0 = (0, -1, 128) + BSGS_STEPS
+    loaded = []
+    for s in steps0:
+        elt = orc.galois_elt(s)
+        k = keys.galois_key(elt)
+        orc.load_ksk(0, elt, k)
+        loaded.append((0, elt, k))
+    for s in [1, -1, 2, -2, 4, -4, 8, -8, 16, -16, 32, -32]:  # a power-of-two "default" set for NAF chains
+        elt = orc.galois_elt(s)
+        k = keys.galois_key(elt)
+        orc.load_ksk(1, elt, k)
+        loaded.append((1, elt, k))
+    rk = keys.relin_key()
+    orc.load_ksk(2, 0, rk)
+    loaded.append((2, 0, rk))
+    rng = np.random.default_rng(7)
+    cts = [keys.encrypt_zero_plus(orc, orc.encode(rng.integers(0, common.T, N, dtype=np.uint64))) for _ in range(3)]
+    return dict(q=q, orc=orc, keys=keys, loaded=loaded, cts=np.stack(cts), rng=rng)
+
+
+@pytest.fixture(scope="module", params=BACKENDS)
+def eng(request, world):
+    ctx = make_ctx(request.param, N, world["q"])
+    for kind, elt, k in world["loaded"]:
+        ctx.load_ksk(kind, elt, k)
+    yield ctx
+    ctx.close()
+
+
+def test_constants(eng, world):
+    c, o = eng.constants(), world["orc"]
+    assert np.array_equal(c["psi"], o.ntt_roots()[0]) and c["psi_t"] == o.ntt_roots()[1]
+    b = o.behz()
+    assert c["m_sk"] == b["m_sk"] and c["gamma"] == b["gamma"] and np.array_equal(c["base_B"], b["base_B"])
+    assert np.array_equal(c["bsk_roots"], b["bsk_roots"])
+    for s in (0, 1, -1, 128, -300, 511):
+        assert eng.galois_elt(s) == o.galois_elt(s)
+
+
+def test_ntt_every_modulus(eng, world):
+    o, rng = world["orc"], np.random.default_rng(0)
+    for limb in range(2 * o.K):
+        mod = int(o.q[limb]) if limb < o.K else int(o.behz()["base_B"][limb - o.K]) if limb - o.K < o.L else o.behz()["m_sk"]
+        x = rng.integers(0, mod, (2, N), dtype=np.uint64)
+        x[0, :4] = [0, mod - 1, 1, mod - 1]  # edge residues
+        f = eng.ntt(limb, x)
+        assert np.array_equal(f, np.stack([o.ntt(limb, v) for v in x])), limb
+        assert np.array_equal(eng.ntt(limb, f, inverse=True), x), limb
+
+
+def test_encode(eng, world):
+    o, rng = world["orc"], np.random.default_rng(1)
+    sl = rng.integers(0, common.T, N, dtype=np.uint64)
+    for n in (N, 300, 129, 1):
+        assert np.array_equal(eng.encode(sl[:n]), o.encode(sl[:n]))
+    sparse = np.zeros(N // 2 + 128, dtype=np.uint64)
+    sparse[:128] = sl[:128]
+    sparse[N // 2:] = sl[128:256]
+    assert np.array_equal(eng.encode(sparse), o.encode(sparse))
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.encode(np.array([common.T], dtype=np.uint64))
+
+
+def test_elementwise(eng, world):
+    o, cts = world["orc"], world["cts"]
+    pt = o.encode(np.random.default_rng(2).integers(0, common.T, 700, dtype=np.uint64))
+    assert np.array_equal(eng.add(cts[0], cts[1]), o.add(cts[0], cts[1]))
+    assert np.array_equal(eng.negate(cts[0]), o.negate(cts[0]))
+    z = np.zeros_like(cts[0])
+    assert np.array_equal(eng.negate(z), z)
+    assert np.array_equal(eng.add_plain(cts[0], pt), o.add_plain(cts[0], pt))
+    assert np.array_equal(eng.multiply_plain(cts[0], pt), o.multiply_plain(cts[0], pt))
+    both = eng.add(cts[:2], cts[1:3])
+    assert np.array_equal(both[0], o.add(cts[0], cts[1])) and np.array_equal(both[1], o.add(cts[1], cts[2]))
+    with pytest.raises(pkg.HheLogicError):
+        eng.multiply_plain(cts[0], np.zeros(N, dtype=np.uint64))
+
+
+def test_rotations(eng, world):
+    o, cts = world["orc"], world["cts"]
+    for s, ks in ((-1, 0), (128, 0), (-16, 0), (-112, 0), (1, 1), (-5, 1), (7, 1), (-27, 1), (31, 1)):
+        assert np.array_equal(eng.rotate_rows(cts[0], s, ks), o.rotate_rows(cts[0], s, ks)), s
+    assert np.array_equal(eng.rotate_rows(cts[0], 0, 0), cts[0])
+    assert np.array_equal(eng.rotate_columns(cts[1]), o.rotate_columns(cts[1]))
+    got = eng.rotate_rows(cts, -1, 0)
+    assert all(np.array_equal(got[i], o.rotate_rows(cts[i], -1, 0)) for i in range(3))
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.rotate_rows(cts[0], -64, 1)  # single-term NAF without a key: "Galois key not present"
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.rotate_rows(cts[0], N // 2, 0)  # step count too large
+
+
+def test_multiply_relinearize(eng, world):
+    o, cts = world["orc"], world["cts"]
+    m3 = o.multiply(cts[0], cts[1])
+    assert np.array_equal(eng.multiply(cts[0], cts[1]), m3)
+    assert np.array_equal(eng.square(cts[2]), o.multiply(cts[2], cts[2]))
+    assert np.array_equal(eng.relinearize(m3), o.relinearize(m3))
+    assert np.array_equal(eng.exponentiate3(cts[0]), o.exponentiate3(cts[0]))
+    got = eng.multiply(cts[:2], cts[1:3])
+    assert np.array_equal(got[1], o.multiply(cts[1], cts[2]))
+
+
+def test_vec_sum_mask_flatten_fc(eng, world):
+    o, cts = world["orc"], world["cts"]
+    for n in (1, 2, 20, 40):
+        assert np.array_equal(eng.vec_sum(cts[0], n, 1), o.vec_sum(cts[0], n, 1)), n
+    ones = np.ones(44, dtype=np.uint64)
+    assert np.array_equal(eng.mask(cts[0], ones), o.mask(cts[0], ones))
+    fc = eng.fc_rows(cts[:2], cts[1:3], 24, 1)
+    for s in range(2):
+        for r in range(2):
+            want = o.vec_sum(o.relinearize(o.multiply(cts[s], cts[1 + r])), 24, 1)
+            assert np.array_equal(fc[s, r], want)
+
+
+def test_round_material(eng):
+    for ctr, layer in ((0, 0), (0, 3), (5, 1), (2**40 + 3, 2)):
+        got = eng.pasta_layer_material(common.NONCE, ctr, layer)
+        want = O.pasta_layer_material(common.T, common.NONCE, ctr, layer)
+        assert all(np.array_equal(g, w) for g, w in zip(got, want))
+
+
+@pytest.mark.parametrize("bsgs", [False, True])
+def test_transciphering_vs_oracle(eng, world, bsgs):
+    o, keys, rng = world["orc"], world["keys"], np.random.default_rng(11)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    pt = rng.integers(0, common.T, 300, dtype=np.uint64)  # 3 blocks, last one ragged (44 words)
+    sym = O.pasta_plain(key, common.T, pt)
+    ek = keys.encrypt_zero_plus(o, o.encode(common.pack_key(key, N)))
+    got = eng.pasta3_decompose(ek, sym, use_bsgs=bsgs)
+    want = o.pasta_decompose(ek, sym, use_bsgs=bsgs)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    if not bsgs:
+        # records API: two records restart the counters (CSP.cpp:247-252) -> same ciphertexts as two separate calls
+        two = eng.pasta3_decompose(ek, np.concatenate([sym[:256], sym[:256]]), records=2)
+        assert np.array_equal(two[:2], want[:2]) and np.array_equal(two[2:], want[:2])
+        # first_counter shifts the SHAKE stream
+        assert np.array_equal(eng.pasta3_decompose(ek, sym[128:256], first_counter=1)[0], want[1])
+
+
+# ---- golden vectors generated from the reference itself ---------------------------------------------------------------
+@pytest.fixture(scope="module", params=BACKENDS)
+def eng512(request):
+    ctx = make_ctx(request.param, int(FX["N"]), FX["q"])
+    for name, kind in (("gk_m1", 0), ("gk_p128", 0), ("gk_col", 0), ("rk", 2)):
+        ctx.load_ksk(kind, int(FX[name + "_elt"]), FX[name])
+    yield ctx
+    ctx.close()
+
+
+def test_golden_primitives(eng512):
+    e, a, b, pt = eng512, FX["ct_a"], FX["ct_b"], FX["pt"]
+    assert np.array_equal(e.ntt(0, a[0, 0]), FX["kat_ntt_fwd"])
+    assert np.array_equal(e.ntt(3, a[1, 3], inverse=True), FX["kat_ntt_inv"])
+    assert np.array_equal(e.encode(FX["slots_p"]), pt)
+    assert np.array_equal(e.add(a, b), FX["kat_add"])
+    assert np.array_equal(e.negate(a), FX["kat_negate"])
+    assert np.array_equal(e.add_plain(a, pt), FX["kat_add_plain"])
+    assert np.array_equal(e.multiply_plain(a, pt), FX["kat_multiply_plain"])
+    assert np.array_equal(e.rotate_rows(a, -1), FX["kat_rot_m1"])
+    assert np.array_equal(e.rotate_rows(a, 128), FX["kat_rot_p128"])
+    assert np.array_equal(e.rotate_columns(a), FX["kat_rot_col"])
+    assert np.array_equal(e.multiply(a, b), FX["kat_multiply"])
+    assert np.array_equal(e.square(a), FX["kat_square"])
+    assert np.array_equal(e.relinearize(FX["kat_multiply"]), FX["kat_relin"])
+    assert np.array_equal(e.exponentiate3(a), FX["kat_exp3"])
+    assert np.array_equal(e.mask(a, np.ones(44, dtype=np.uint64)), FX["kat_mask"])
+
+
+def test_golden_material(eng512):
+    for tag, ctr, layer in (("c0l0", 0, 0), ("c0l3", 0, 3), ("c5l1", 5, 1)):
+        m1, m2, rc = eng512.pasta_layer_material(common.NONCE, ctr, layer)
+        assert np.array_equal(m1, FX["mat1_" + tag]) and np.array_equal(m2, FX["mat2_" + tag]) and np.array_equal(rc, FX["rc_" + tag])
+
+
+def test_golden_transciphering(eng512):
+    got = eng512.pasta3_decompose(FX["enc_key"], FX["sym_ct"])
+    assert np.array_equal(got, FX["decomposed"])

@@ -1,0 +1,89 @@
+"""Full-size (BASELINE.json: N=16384, t=65537, BFVDefault) parity on the B200 against the reference itself
+(oracle/_ref/libhhe_ref.so: unmodified reference sources + vendored libseal, prebuilt in the container)."""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+from oracle import refshim as R
+
+pkg = common.package()
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="oracle/_ref/libhhe_ref.so not built")]
+N = 16384
+
+
+@pytest.fixture(scope="module")
+def world():
+    ref = R.Ref(N, common.T, None, seed=3, steps=(0, -1, 128), default_gk=False)
+    assert list(ref.q) == common.Q_16384
+    ctx = pkg.Context(N, common.T, ref.q, device=0)
+    common.load_keys_from_ref(ctx, ref, keysets=(0,))
+    rng = np.random.default_rng(5)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    yield dict(ref=ref, ctx=ctx, rng=rng, key=key, enc_key=ref.encrypt(common.pack_key(key, N)))
+    ctx.close()
+    ref.close()
+
+
+def test_constants_equal_seal(world):
+    ref, ctx = world["ref"], world["ctx"]
+    c, rb = ctx.constants(), ref.behz()
+    assert np.array_equal(c["psi"], ref.ntt_roots()[0]) and c["psi_t"] == ref.ntt_roots()[1]
+    assert c["m_sk"] == rb["m_sk"] and np.array_equal(c["base_B"], rb["base_B"]) and np.array_equal(c["bsk_roots"], rb["bsk_roots"])
+
+
+def test_ntt_all_limbs(world):
+    ref, ctx, rng = world["ref"], world["ctx"], world["rng"]
+    for limb in range(ref.K):
+        x = rng.integers(0, int(ref.q[limb]), N, dtype=np.uint64)
+        f = ctx.ntt(limb, x)
+        assert np.array_equal(f, ref.ntt(limb, x))
+        assert np.array_equal(ctx.ntt(limb, f, inverse=True), x)
+
+
+def test_primitives(world):
+    ref, ctx, rng = world["ref"], world["ctx"], world["rng"]
+    a = ref.encrypt(rng.integers(0, common.T, N, dtype=np.uint64))
+    b = ref.encrypt(rng.integers(0, common.T, N, dtype=np.uint64))
+    pt = ref.encode(rng.integers(0, common.T, 9000, dtype=np.uint64))
+    assert np.array_equal(ctx.add_plain(a, pt), ref.add_plain(a, pt))
+    assert np.array_equal(ctx.multiply_plain(a, pt), ref.multiply_plain(a, pt))
+    assert np.array_equal(ctx.rotate_rows(a, -1), ref.rotate_rows(a, -1))
+    assert np.array_equal(ctx.rotate_rows(a, 128), ref.rotate_rows(a, 128))
+    assert np.array_equal(ctx.rotate_columns(a), ref.rotate_columns(a))
+    m3 = ref.multiply(a, b)
+    assert np.array_equal(ctx.multiply(a, b), m3)
+    assert np.array_equal(ctx.relinearize(m3), ref.relinearize(m3))
+    assert np.array_equal(ctx.exponentiate3(a), ref.exponentiate3(a))
+
+
+def test_one_block_bit_exact_with_seal(world):
+    """BASELINE.json configs[0]: HE_decrypt of one 128-element block at N=16384."""
+    ref, ctx, rng, key = world["ref"], world["ctx"], world["rng"], world["key"]
+    pt = rng.integers(0, common.T, 128, dtype=np.uint64)
+    sym = O.pasta_plain(key, common.T, pt)
+    want = ref.pasta_decompose(world["enc_key"], sym, use_bsgs=False)
+    got = ctx.pasta3_decompose(world["enc_key"], sym, use_bsgs=False)
+    assert np.array_equal(got, want)
+    slots, budget = ref.decrypt(got[0])
+    assert budget > 60 and np.array_equal(slots[:128], pt)
+    assert not slots[128:8192].any() and not slots[8320:].any()  # SURVEY B.3 slot layout
+
+
+def test_batch_and_counter_invariance(world):
+    """Size-independent property: a block's ciphertext depends only on (counter, words), not on how it was batched."""
+    ref, ctx, rng, key = world["ref"], world["ctx"], world["rng"], world["key"]
+    pt = rng.integers(0, common.T, 5 * 128 - 30, dtype=np.uint64)
+    sym = O.pasta_plain(key, common.T, pt)
+    ctx.set_batch(0)
+    full = ctx.pasta3_decompose(world["enc_key"], sym)
+    ctx.set_batch(2)
+    split = ctx.pasta3_decompose(world["enc_key"], sym)
+    ctx.set_batch(0)
+    assert np.array_equal(full, split)
+    one = ctx.pasta3_decompose(world["enc_key"], sym[3 * 128:4 * 128], first_counter=3)
+    assert np.array_equal(one[0], full[3])
+    for b in (0, 4):
+        slots, _ = ref.decrypt(full[b])
+        n = min(128, len(pt) - b * 128)
+        assert np.array_equal(slots[:n], pt[b * 128:b * 128 + n])
