@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- PASTA-3 blocks transciphered per second at BFV N=16384, t=65537 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--blocks B] [--bsgs] [--impl reference]
+
+A "step" transciphers B PASTA-3 blocks with distinct SHAKE counters per GPU (BASELINE.json configs[3], the
+SpO2-stream case, sharded: rank r, step s owns counters [(s*G + r)*B, (s*G + r + 1)*B)); work per GPU is fixed as
+N grows (weak scaling). Independent blocks need no data-path collective; rank 0 only gathers one 64-bit digest per
+block over NCCL at the end of every step.
+
+  value  : blocks/s with the symmetric ciphertext and the encrypted key already resident in HBM (CUDA events on the
+           engine's stream, max over ranks).
+  e2e    : the same metric through the host-buffer C ABI call hhe_pasta3_decompose (pinned host buffers; H2D of the
+           inputs and D2H of every output ciphertext inside the timed region).
+  roofline: the dominant kernel (ks_digits, the key-switch digit NTT + inner product) timed live with CUDA events.
+  cpu_baseline / --impl reference: the UNMODIFIED reference (src/pasta + vendored libseal via oracle/_ref) on all host
+           cores, one PASTA_SEAL per thread, one block per thread per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import common  # noqa: E402
+
+N = 16384
+METRIC = "pasta3_blocks_transciphered_per_s"
+UNIT = "blocks/s"
+MIB = 1 << 20
+# algorithmic bytes per PASTA-3 block (operands read once + result written once per SEAL-level op)
+BYTES_PER_BLOCK = {False: 7_751_991_296, True: 5_990_383_616}
+KS_BYTES = 4 * MIB  # one key switch (rotate_rows / rotate_columns): 2 ciphertexts
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config(args, world):
+    return {
+        "workload": f"BASELINE configs[3] shard: {args.blocks} distinct-counter PASTA-3 blocks per GPU per step, "
+                    f"{'BSGS' if args.bsgs else 'diagonal (reference default use_bsgs=false)'} affine layers",
+        "N": N, "t": common.T, "coeff_modulus": "BFVDefault(16384): L=8 data limbs + special prime",
+        "blocks_per_gpu_per_step": args.blocks, "use_bsgs": bool(args.bsgs), "parallelism": f"shard{world}",
+        "l2": "working set per step (>=0.6 GB of ciphertext state + 144 MB of key-switching keys) exceeds the 126 MB L2",
+    }
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    from oracle import refshim as R
+    if not R.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhhe_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    steps = [0, -1, 128] + ([-16 * k for k in range(1, 8)] if args.bsgs else [])
+    ref = R.Ref(N, common.T, None, seed=4, steps=tuple(steps), default_gk=False)
+    rng = np.random.default_rng(4)
+    enc_key = ref.encrypt(common.pack_key(rng.integers(0, common.T, 256, dtype=np.uint64), N))
+    per = max(1, args.ref_blocks_per_thread)
+    for _ in range(args.warmup):
+        ref.bench_decompose(enc_key, cores, per, args.bsgs)
+    total = 0.0
+    for _ in range(args.steps):
+        total += ref.bench_decompose(enc_key, cores, per, args.bsgs)
+    value = cores * per * args.steps / total
+    sample = f"{cores} threads x {per} block(s) per step, one pasta::PASTA_SEAL per thread (src/pasta/pasta_3_seal.cpp:106-172 + libseal-4.0.a)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--blocks", type=int, default=296, help="PASTA blocks per GPU per step")
+    ap.add_argument("--bsgs", action="store_true", help="baby-step/giant-step affine layers (reference: use_bsgs=true)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-blocks-per-thread", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import refshim as R
+    ref_ok = R.available()
+    pkg = common.package()
+    stream = torch.cuda.Stream()
+    ctx = pkg.Context(N, common.T, common.Q_16384, device=local, stream=stream.cuda_stream)
+    ctx.set_batch(args.blocks)
+    L = ctx.L
+    B = args.blocks
+
+    # ---- inputs: rank 0 generates the key material, NCCL broadcasts it (one-time, untimed) ----
+    ref = None
+    nkeys = 4 + (7 if args.bsgs else 0)
+    key_t = torch.empty((nkeys, L, 2, L + 1, N), dtype=torch.int64, device="cuda")
+    elt_t = torch.empty((nkeys, 2), dtype=torch.int64, device="cuda")
+    ek_t = torch.empty((2, L, N), dtype=torch.int64, device="cuda")
+    sk_t = torch.empty(256, dtype=torch.int64, device="cuda")
+    if rank == 0:
+        steps_ = [0, -1, 128] + ([-16 * k for k in range(1, 8)] if args.bsgs else [])
+        rng0 = np.random.default_rng(4)
+        sym_key = rng0.integers(0, common.T, 256, dtype=np.uint64)
+        if ref_ok:
+            ref = R.Ref(N, common.T, None, seed=4, steps=tuple(steps_), default_gk=False)
+            ks = [(0, ref.galois_elt(s), ref.ksk(0, ref.galois_elt(s))) for s in steps_] + [(2, 0, ref.ksk(2))]
+            enc_key = ref.encrypt(common.pack_key(sym_key, N))
+        else:
+            q = common.Q_16384
+            def rnd_key():
+                k = np.empty((L, 2, L + 1, N), dtype=np.uint64)
+                for i, m in enumerate(q):
+                    k[:, :, i, :] = rng0.integers(0, m, (L, 2, N), dtype=np.uint64)
+                return k
+            ks = [(0, ctx.galois_elt(s), rnd_key()) for s in steps_] + [(2, 0, rnd_key())]
+            enc_key = np.stack([np.stack([rng0.integers(0, m, N, dtype=np.uint64) for m in q[:L]]) for _ in range(2)])
+        for i, (kind, elt, k) in enumerate(ks):
+            key_t[i].copy_(torch.from_numpy(k.view(np.int64)))
+            elt_t[i, 0], elt_t[i, 1] = kind, elt
+        ek_t.copy_(torch.from_numpy(enc_key.view(np.int64)))
+        sk_t.copy_(torch.from_numpy(sym_key.view(np.int64)))
+    if world > 1:
+        for t_ in (key_t, elt_t, ek_t, sk_t):
+            dist.broadcast(t_, 0)
+    elts = elt_t.cpu().numpy()
+    for i in range(nkeys):
+        ctx.load_ksk(int(elts[i, 0]), int(elts[i, 1]), key_t[i].cpu().numpy().view(np.uint64))
+    del key_t
+    enc_key = ek_t.cpu().numpy().view(np.uint64)
+    sym_key = sk_t.cpu().numpy().view(np.uint64)
+
+    # synthetic symmetric ciphertext stream for this rank (uniform words < t, seed 4 + rank)
+    rng = np.random.default_rng(1000 + rank)
+    sym_host = torch.empty((B, 128), dtype=torch.int64).pin_memory()
+    sym_np = sym_host.numpy().view(np.uint64)
+    sym_np[:] = rng.integers(0, common.T, (B, 128), dtype=np.uint64)
+    out_host = torch.empty((B, 2, L, N), dtype=torch.int64).pin_memory()
+    d_sym = sym_host.cuda()
+    d_key = ek_t
+    d_out = torch.empty((B, 2, L, N), dtype=torch.int64, device="cuda")
+    lens = np.full(B, 128, dtype=np.uint32)
+    digests = torch.empty((world, B), dtype=torch.int64, device="cuda") if rank == 0 else None
+    import ctypes as C
+    ptr = lambda t_: C.c_void_p(t_.data_ptr())  # noqa: E731
+
+    def counters(step):
+        base = (step * world + rank) * B
+        return np.arange(base, base + B, dtype=np.uint64)
+
+    def device_step(step):
+        ctx.dev_pasta3_decompose(ptr(d_key), ptr(d_sym), lens, counters(step), common.NONCE, args.bsgs, ptr(d_out))
+        with torch.cuda.stream(stream):
+            dig = d_out.view(B, -1).sum(dim=1)
+            if world > 1:
+                dist.gather(dig, list(digests.unbind(0)) if rank == 0 else None, dst=0)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- correctness spot-check (untimed): block 0 of step 0 must decrypt to the PASTA plaintext ----
+    checked = "skipped (oracle/_ref absent: random key material)"
+    for s in range(args.warmup):
+        device_step(s)
+        if s == 0 and rank == 0 and ref is not None:
+            ctx.sync()
+            from oracle import oracle as O
+            got = d_out[0].cpu().numpy().view(np.uint64)
+            slots, budget = ref.decrypt(got)
+            want = O.pasta_plain(sym_key, common.T, sym_np[0], decrypt=True)  # counter 0
+            assert np.array_equal(slots[:128], want), "bench output does not decrypt to the PASTA plaintext"
+            checked = f"block 0 decrypts (SEAL) to the PASTA plaintext, noise budget {budget} bits"
+
+    # ---- timed region: K device-resident steps ----
+    ctx.profile(True)
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.steps):
+        device_step(args.warmup + s)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count() - l0
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    def host_step(step):
+        first = int(counters(step)[0])
+        rc = ctx.lib.hhe_pasta3_decompose(ctx.h, C.cast(C.c_void_p(ek_host.data_ptr()), C.POINTER(C.c_uint64)),
+                                          C.cast(C.c_void_p(sym_host.data_ptr()), C.POINTER(C.c_uint64)), C.c_size_t(B * 128),
+                                          C.c_uint64(common.NONCE), C.c_uint64(first), int(args.bsgs),
+                                          C.cast(C.c_void_p(out_host.data_ptr()), C.POINTER(C.c_uint64)))
+        ctx._chk(rc)
+    ek_host = torch.from_numpy(enc_key.view(np.int64).copy()).pin_memory()
+    host_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        host_step(args.warmup + s)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t_e.item())
+    if ref is not None and rank == 0:
+        same = np.array_equal(out_host[0].numpy().view(np.uint64), d_out[0].cpu().numpy().view(np.uint64))
+        assert same, "host-API and device-API outputs differ"
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = peak_hbm()
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    ks = prof.get("ks_digits", {"launches": 0, "ms": 0.0})
+    avg_ms = ks["ms"] / max(1, ks["launches"])
+    achieved = KS_BYTES * B / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ks_digits_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_at_bench_batch")
+    kernel_ms = sum(v["ms"] for v in prof.values())
+    roofline = {
+        "bound": "hbm", "kernel": "ks_digits (key-switch digit NTT + key inner product)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": KS_BYTES * B, "avg_launch_ms": avg_ms, "launches": ks["launches"],
+        "share_of_kernel_time": ks["ms"] / kernel_ms if kernel_ms else None, "dominant_by_time": dom[0],
+        "note": "64-bit modular-integer kernel: bounded by the INT32/IMAD pipe, not HBM (see DESIGN.md, profiles/)",
+        "step_level": {"algorithmic_bytes_per_block": BYTES_PER_BLOCK[bool(args.bsgs)],
+                       "achieved": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9,
+                       "frac": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9 / peak},
+        "kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    # ---- CPU baseline: the reference itself on this box's host cores (bounded sample) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        if ref is not None:
+            secs = ref.bench_decompose(enc_key, cores, 1, args.bsgs)
+            cpu = {"value": cores / secs, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"{cores} threads x 1 block, one pasta::PASTA_SEAL per thread (reference sources + libseal-4.0.a), {secs:.1f} s"}
+        else:
+            from oracle import oracle as O
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "oracle/_ref absent; run tests for the port"}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": config(args, world), "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ek_host.numel() * 8 + sym_host.numel() * 8 + B * 12),
+                "d2h_bytes_per_step": int(out_host.numel() * 8)},
+        "gpu_launches": int(launches), "clocks": clocks, "verified": checked,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

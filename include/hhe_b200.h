@@ -121,6 +121,11 @@ int hhe_dev_pasta3_decompose(hhe_ctx *ctx, const uint64_t *d_enc_key, const uint
                              const uint64_t *counters, size_t nblocks, uint64_t nonce, int use_bsgs, uint64_t *d_out);
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 uint64_t hhe_launch_count(const hhe_ctx *ctx);
+/* Per-kernel device time: when enabled every launch is bracketed by CUDA events on the context's stream.
+ * hhe_profile_report writes a JSON object {"kernel": {"launches": n, "ms": t}, ...} into buf (NUL-terminated). */
+int hhe_profile_enable(hhe_ctx *ctx, int on);
+int hhe_profile_reset(hhe_ctx *ctx);
+int hhe_profile_report(hhe_ctx *ctx, char *buf, size_t cap);
 
 /* ---- plain PASTA-3 material (device SHAKE128 + matrix generation, for parity tests of that kernel) ---- */
 /* mat1[128*128], mat2[128*128], rc[256] as u32 for (nonce, counter, layer 0..3) */

@@ -29,7 +29,7 @@ SYMBOLS = [
     "hhe_pasta3_decompose_records", "hhe_mask", "hhe_flatten", "hhe_vec_sum", "hhe_fc_rows", "hhe_dev_alloc",
     "hhe_dev_free", "hhe_dev_upload", "hhe_dev_download", "hhe_sync", "hhe_dev_ntt", "hhe_dev_rotate_rows",
     "hhe_dev_relinearize", "hhe_dev_multiply", "hhe_dev_pasta3_decompose", "hhe_launch_count",
-    "hhe_pasta_layer_material",
+    "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report",
 ]
 
 
@@ -129,6 +129,18 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.hhe_launch_count(self.h))
+
+    def profile(self, on=True):
+        self._chk(self.lib.hhe_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._chk(self.lib.hhe_profile_reset(self.h))
+
+    def profile_report(self):
+        import json
+        buf = C.create_string_buffer(16384)
+        self._chk(self.lib.hhe_profile_report(self.h, buf, C.c_size_t(len(buf))))
+        return json.loads(buf.value.decode())
 
     def galois_elt(self, step):
         return int(self.lib.hhe_galois_elt(self.h, step))

@@ -136,6 +136,31 @@ int hhe_has_ksk(const hhe_ctx *ctx, int kind, uint32_t galois_elt) {
 
 uint64_t hhe_launch_count(const hhe_ctx *ctx) { return ctx && ctx->eng ? ctx->eng->dev().launches : 0; }
 
+int hhe_profile_enable(hhe_ctx *ctx, int on) {
+  return guarded([&] {
+    E(ctx).dev().profile_resolve();
+    E(ctx).dev().profiling = on != 0;
+  });
+}
+int hhe_profile_reset(hhe_ctx *ctx) {
+  return guarded([&] { E(ctx).dev().profile_reset(); });
+}
+int hhe_profile_report(hhe_ctx *ctx, char *buf, size_t cap) {
+  return guarded([&] {
+    Device &d = E(ctx).dev();
+    d.profile_resolve();
+    std::string js = "{";
+    for (size_t i = 0; i < d.stats.size(); ++i) {
+      if (i) js += ", ";
+      js += "\"" + std::string(d.stats[i].name) + "\": {\"launches\": " + std::to_string(d.stats[i].launches) +
+            ", \"ms\": " + std::to_string(d.stats[i].ms) + "}";
+    }
+    js += "}";
+    if (js.size() + 1 > cap) throw std::invalid_argument("profile report buffer too small");
+    std::memcpy(buf, js.c_str(), js.size() + 1);
+  });
+}
+
 // ---------------------------------------------------------------------------------------------- primitives
 int hhe_ntt(hhe_ctx *ctx, int limb, int inverse, uint64_t *data, size_t count) {
   return guarded([&] {

@@ -117,6 +117,7 @@ struct ShakeStream {
 // Phase 2: rows 1..127 by the companion recurrence row_i[j] = first[j]*row_{i-1}[127] + row_{i-1}[j-1] mod p,
 //          thread j owns column j of one of the 8 matrices (256 threads = 2 matrices at a time).
 struct MaterialBody {
+  static constexpr const char *kName = "pasta_material";
   const u64 *counters;  // [blocks]
   u64 nonce;
   u32 *out;  // [blocks][kMaterialWords]

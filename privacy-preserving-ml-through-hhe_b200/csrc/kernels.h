@@ -23,6 +23,7 @@ struct TabMap {  // limb index inside an item -> NTT table id
 // Replaces seal::util::ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (seal/util/ntt.h:195-340).
 template <int LOGS>
 struct NttBody {
+  static constexpr const char *kName = "ntt";
   const u64 *in;
   u64 *out;
   const DevConsts *C;
@@ -65,6 +66,7 @@ struct NttBody {
 // Grid order puts b fastest so co-resident CTAs read the same key tile from L2.
 template <int LOGH>
 struct KsDigitsBody {
+  static constexpr const char *kName = "ks_digits";
   const u64 *target;  // [count][..] : item b's target polynomial (L limbs) at target + b*stride
   size_t stride;
   const W2 *key;  // [L][2][K][N]
@@ -135,6 +137,7 @@ struct KsDigitsBody {
 //   out[c][i] = ( acc[c][i] - (r_c mod q_i) + (half mod q_i) ) * q_sp^-1  +  base_c[i],  r_c = acc[c][sp] + half mod q_sp
 // acc is in coefficient form (after the inverse NTT). base1 may be NULL (rotations: component 1 starts from zero).
 struct ModDownBody {
+  static constexpr const char *kName = "moddown";
   const u64 *acc;    // [count][2][K][N]
   const u64 *base0;  // item b at base0 + b*bstride : [L][N]
   const u64 *base1;
@@ -174,6 +177,7 @@ struct ModDownBody {
 // GaloisTool::apply_galois on coefficient-form ciphertexts (seal/util/galois.h:32-33), gather form:
 //   out[idx] = +-in[i],  i*elt = idx or idx+N (mod 2N)  <=>  i' = idx*elt^-1 mod 2N, i = i' mod N, sign = i' >= N
 struct GaloisBody {
+  static constexpr const char *kName = "galois";
   const u64 *in;  // [count][2][L][N]
   u64 *out;
   const DevConsts *C;
@@ -197,7 +201,8 @@ struct GaloisBody {
 
 // ------------------------------------------------------------------------------------------------------------
 // Element-wise ciphertext ops (Evaluator::add / negate / add_plain, seal/evaluator.h:92,118,665)
-struct AddBody {  // out = a + b (optionally a + b where b has item stride 0)
+struct AddBody {  // out = a + b
+  static constexpr const char *kName = "add";
   const u64 *a, *b;
   u64 *out;
   const DevConsts *C;
@@ -216,6 +221,7 @@ struct AddBody {  // out = a + b (optionally a + b where b has item stride 0)
 };
 
 struct NegateBody {
+  static constexpr const char *kName = "negate";
   const u64 *a;
   u64 *out;
   const DevConsts *C;
@@ -232,6 +238,7 @@ struct NegateBody {
 // out = (negate ? -a : a) + Delta-scaled plaintext on component 0 (multiply_add_plain_with_scaling_variant):
 //   c0[j] += m_j*floor(Q/t) + floor((m_j*(Q mod t) + (t+1)/2) / t)
 struct AddPlainBody {
+  static constexpr const char *kName = "add_plain";
   const u64 *a;   // [count][2][L][N]
   const u64 *pt;  // [count][N], item stride pstride (0 = shared)
   size_t pstride;
@@ -264,6 +271,7 @@ struct AddPlainBody {
 };
 
 struct BroadcastBody {  // out[item] = src for every item
+  static constexpr const char *kName = "broadcast";
   const u64 *src;
   u64 *out;
   size_t words, total;
@@ -291,6 +299,7 @@ constexpr size_t kMaterialWords = kMatWords + 4 * 2 * kPastaT;
 
 template <int LOGS>
 struct EncodeBody {
+  static constexpr const char *kName = "encode";
   const u64 *slots;
   size_t sstride;
   const u32 *lens;  // per item valid count (NULL: n)
@@ -359,6 +368,7 @@ struct EncodeBody {
 // grid = items * L
 template <int LOGS>
 struct LiftNttBody {
+  static constexpr const char *kName = "lift_ntt";
   const u64 *pt;  // [items][N]
   u64 *out;       // [items][L][N]
   const DevConsts *C;
@@ -391,6 +401,7 @@ struct LiftNttBody {
 // (the PASTA diagonal loop sums 128 such products; accumulation before the single inverse NTT is exact)
 template <int LOGS>
 struct NttMacBody {
+  static constexpr const char *kName = "ntt_mac";
   const u64 *ct;  // [items][2][L][N] coefficient form
   const u64 *D;   // [items][L][N] (dstride = L*N) or shared (dstride = 0)
   size_t dstride;
@@ -428,6 +439,7 @@ struct NttMacBody {
 
 // fastbconv_m_tilde + sm_mrq: x (base q, coefficient form) -> x in base Bsk.  One thread per (poly, coefficient).
 struct BehzExtendBody {
+  static constexpr const char *kName = "behz_extend";
   const u64 *x;  // [polys][L][N]
   u64 *xb;       // [polys][L+1][N]
   const DevConsts *C;
@@ -462,6 +474,7 @@ struct BehzExtendBody {
 // NTT-domain tensor product for one base: d0 = a0 b0, d1 = a0 b1 + a1 b0, d2 = a1 b1.
 // a, b: [items][2][limbs][N]; d: [items][3][limbs][N]; table id of limb l is tab0 + l.
 struct TensorBody {
+  static constexpr const char *kName = "behz_tensor";
   const u64 *a, *b;
   u64 *d;
   const DevConsts *C;
@@ -488,6 +501,7 @@ struct TensorBody {
 
 // multiply by t, fast_floor, fastbconv_sk: (d in base q, d in base Bsk; coefficient form) -> round(t*d/Q) in base q
 struct BehzScaleRoundBody {
+  static constexpr const char *kName = "behz_scale_round";
   const u64 *dq;  // [polys][L][N]
   const u64 *db;  // [polys][L+1][N]
   u64 *out;       // [polys][L][N]
@@ -532,6 +546,7 @@ struct BehzScaleRoundBody {
 
 // value -> (value, floor(value * 2^64 / q)) for uploaded key-switching keys (one-time, at hhe_load_ksk)
 struct ShoupifyBody {
+  static constexpr const char *kName = "shoupify";
   const u64 *in;  // [L][2][K][N]
   W2 *out;
   const DevConsts *C;

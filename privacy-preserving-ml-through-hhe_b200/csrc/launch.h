@@ -29,13 +29,66 @@ __global__ void __launch_bounds__(512) kernel_entry(const Body body) {
 }
 #endif
 
+// Per-kernel device-time accounting (hhe_profile_*): when enabled every launch is bracketed by CUDA events on the
+// launching stream; durations are resolved lazily after a stream sync. Used by bench.py for the live roofline figure.
+struct KernelStat {
+  const char *name;
+  uint64_t launches;
+  double ms;
+};
+
 struct Device {
 #ifdef HHE_CUDA
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  struct Pending {
+    int kid;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
 #endif
   int sm_count = 1;
   uint64_t launches = 0;
+  bool profiling = false;
+  std::vector<KernelStat> stats;
+
+  int kernel_id(const char *name) {
+    for (size_t i = 0; i < stats.size(); ++i)
+      if (!std::strcmp(stats[i].name, name)) return static_cast<int>(i);
+    stats.push_back(KernelStat{name, 0, 0.0});
+    return static_cast<int>(stats.size() - 1);
+  }
+  void profile_reset() {
+    profile_resolve();
+    for (auto &s : stats) s.launches = 0, s.ms = 0.0;
+  }
+  void profile_resolve() {
+#ifdef HHE_CUDA
+    if (pending.empty()) return;
+    cuda_check(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    for (auto &p : pending) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, p.a, p.b);
+      stats[p.kid].ms += ms;
+      event_pool.push_back(p.a);
+      event_pool.push_back(p.b);
+    }
+    pending.clear();
+#endif
+  }
+#ifdef HHE_CUDA
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) {
+      cudaEvent_t e = event_pool.back();
+      event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+    return e;
+  }
+#endif
 
   void *dmalloc(size_t bytes) {
 #ifdef HHE_CUDA
@@ -93,7 +146,18 @@ struct Device {
   void launch(const Body &body, size_t grid, int nt, size_t smem_bytes) {
     if (grid == 0) return;
     ++launches;
+    int kid = -1;
+    if (profiling) {
+      kid = kernel_id(Body::kName);
+      ++stats[kid].launches;
+    }
 #ifdef HHE_CUDA
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    if (profiling) {
+      ev_a = get_event();
+      ev_b = get_event();
+      cuda_check(cudaEventRecord(ev_a, stream), "cudaEventRecord");
+    }
     if (smem_bytes > 48 * 1024) {
       static size_t configured = 0;  // per Body instantiation
       if (smem_bytes > configured) {
@@ -105,6 +169,11 @@ struct Device {
     }
     kernel_entry<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
     cuda_check(cudaGetLastError(), "kernel launch");
+    if (profiling) {
+      cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
+      pending.push_back(Pending{kid, ev_a, ev_b});
+      if (pending.size() >= 8192) profile_resolve();
+    }
 #else
     std::vector<unsigned char> smem(smem_bytes + 16);
     for (size_t b = 0; b < grid; ++b) body(static_cast<int>(b), nt, smem.data());
