@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhhe_b200.so")
+LIB_PATH = os.environ.get("HHE_B200_LIB", os.path.join(_HERE, "libhhe_b200.so"))  # override: kernel-variant experiments
 _u64p = C.POINTER(C.c_uint64)
 _u32p = C.POINTER(C.c_uint32)
 

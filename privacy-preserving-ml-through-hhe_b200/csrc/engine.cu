@@ -16,8 +16,8 @@ constexpr int kEwThreads = 256;
 inline size_t ew_grid(size_t total) { return (total + kEwThreads - 1) / kEwThreads; }
 
 inline int ntt_threads(int logS) {
-  int groups = 1 << (logS - 4);
-  return std::max(32, std::min(512, groups));
+  int groups = 1 << (logS - kRadixLog);
+  return std::max(32, std::min(HHE_MAX_THREADS, groups));
 }
 
 TabMap map_mod(int limbs, int period, int base) {

@@ -44,8 +44,9 @@ struct NttBody {
     SYNC();
     if (!inverse) {
       ntt_fwd_core<LOGS>(sm, tw.fwd(tab), q, 1, nt);
+      const DevMod mm = C->mod[tab];
       FOR_THREADS(tid, nt) {
-        for (int i = tid; i < S; i += nt) dst[i] = csub(csub(sm[pidx(i)], q << 1), q);
+        for (int i = tid; i < S; i += nt) dst[i] = barrett64(sm[pidx(i)], mm);
       }
     } else {
       ntt_inv_core<LOGS>(sm, tw.inv(tab), q, 1, nt);
@@ -78,14 +79,17 @@ struct KsDigitsBody {
     constexpr int S = 1 << LOGH;
     const int N = 2 * S;
     const int K = C->K, L = C->L;
-    const int b = bid % count;
-    const int kh = bid / count;
+    // the 2K CTAs of one item are adjacent in the grid: they share the item's digits through L2, and the ~8 items
+    // in flight across the chip sweep the whole (L2-resident) key
+    const int b = bid / (2 * K);
+    const int kh = bid % (2 * K);
     const int k = kh >> 1, h = kh & 1;
     u64 *sm = reinterpret_cast<u64 *>(smem);
     u64 *acc0 = sm + ntt_smem_words(S);
     u64 *acc1 = acc0 + S;
     const DevMod mk = C->mod[k];
-    const u64 q = mk.q, two_q = q << 1;
+    const u64 q = mk.q, two_q = q << 1, nq = 0 - q, four_q = q << 2;
+    const bool wide = q < kWideSlackLimit;
     const W2 *twk = tw.fwd(k);
     const W2 w1 = twk[1];
     FOR_THREADS(tid, nt) {
@@ -95,14 +99,33 @@ struct KsDigitsBody {
       const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
       const bool reduce = C->mod[J].q > q;
       FOR_THREADS(tid, nt) {
-        for (int i = tid; i < S; i += nt) {
-          u64 x = dig[i], y = dig[i + S];
-          if (reduce) {
-            x = barrett64(x, mk);
-            y = barrett64(y, mk);
+        constexpr int U = 8;  // loads in flight per thread (2*U 64-bit requests)
+        for (int i0 = tid; i0 < S; i0 += nt * U) {
+          u64 xs[U], ys[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nt;
+            xs[u] = i < S ? dig[i] : 0;
+            ys[u] = i < S ? dig[i + S] : 0;
           }
-          const u64 t = mul_shoup_lazy(y, w1.w, w1.ws, q);
-          sm[pidx(i)] = h ? x + two_q - t : x + t;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nt;
+            if (i < S) {
+              u64 x = xs[u], y = ys[u];
+              if (reduce) {
+                x = barrett64(x, mk);
+                y = barrett64(y, mk);
+              }
+              if (wide) {
+                const u64 t = mul_shoup_wide(y, w1.w, w1.ws, nq);
+                sm[pidx(i)] = h ? x + four_q - t : x + t;
+              } else {
+                const u64 t = mul_shoup_lazy(y, w1.w, w1.ws, q);
+                sm[pidx(i)] = h ? x + two_q - t : x + t;
+              }
+            }
+          }
         }
       }
       SYNC();
@@ -110,13 +133,19 @@ struct KsDigitsBody {
       const W2 *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
       const W2 *k1 = k0 + static_cast<size_t>(K) * N;
       FOR_THREADS(tid, nt) {
+#pragma unroll 4
         for (int i = tid; i < S; i += nt) {
           const u64 v = sm[pidx(i)];
           const W2 a = k0[i], c = k1[i];
-          u64 s0 = acc0[i] + mul_shoup_lazy(v, a.w, a.ws, q);
-          u64 s1 = acc1[i] + mul_shoup_lazy(v, c.w, c.ws, q);
-          acc0[i] = s0 >= two_q ? s0 - two_q : s0;
-          acc1[i] = s1 >= two_q ? s1 - two_q : s1;
+          if (wide) {  // each term < 4q: L <= 16 digits stay below 64q < 2^63 without reduction
+            acc0[i] += mul_shoup_wide(v, a.w, a.ws, nq);
+            acc1[i] += mul_shoup_wide(v, c.w, c.ws, nq);
+          } else {
+            u64 s0 = acc0[i] + mul_shoup_lazy(v, a.w, a.ws, q);
+            u64 s1 = acc1[i] + mul_shoup_lazy(v, c.w, c.ws, q);
+            acc0[i] = s0 >= two_q ? s0 - two_q : s0;
+            acc1[i] = s1 >= two_q ? s1 - two_q : s1;
+          }
         }
       }
       SYNC();
@@ -125,8 +154,8 @@ struct KsDigitsBody {
     u64 *o1 = o0 + static_cast<size_t>(K) * N;
     FOR_THREADS(tid, nt) {
       for (int i = tid; i < S; i += nt) {
-        o0[i] = csub(acc0[i], q);
-        o1[i] = csub(acc1[i], q);
+        o0[i] = barrett64(acc0[i], mk);
+        o1[i] = barrett64(acc1[i], mk);
       }
     }
   }
@@ -389,8 +418,9 @@ struct LiftNttBody {
     SYNC();
     ntt_fwd_core<LOGS>(sm, tw.fwd(i), q, 1, nt);
     u64 *dst = out + static_cast<size_t>(bid) * S;
+    const DevMod mm = C->mod[i];
     FOR_THREADS(tid, nt) {
-      for (int j = tid; j < S; j += nt) dst[j] = csub(csub(sm[pidx(j)], q << 1), q);
+      for (int j = tid; j < S; j += nt) dst[j] = barrett64(sm[pidx(j)], mm);
     }
   }
 };

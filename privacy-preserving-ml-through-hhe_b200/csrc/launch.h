@@ -15,6 +15,10 @@
 #include <cuda_runtime.h>
 #endif
 
+#ifndef HHE_MAX_THREADS
+#define HHE_MAX_THREADS 1024
+#endif
+
 namespace hhe {
 
 #ifdef HHE_CUDA
@@ -23,7 +27,7 @@ inline void cuda_check(cudaError_t e, const char *what) {
 }
 
 template <class Body>
-__global__ void __launch_bounds__(512) kernel_entry(const Body body) {
+__global__ void __launch_bounds__(HHE_MAX_THREADS) kernel_entry(const Body body) {
   extern __shared__ __align__(16) unsigned char hhe_smem[];
   body(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
 }

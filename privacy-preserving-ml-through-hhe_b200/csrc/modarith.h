@@ -26,6 +26,24 @@ HD u64 mul_shoup(u64 x, u64 w, u64 ws, u64 q) {
 }
 HD u64 mul_shoup(u64 x, W2 c, u64 q) { return mul_shoup(x, c.w, c.ws, q); }
 
+// ---- "wide-slack" arithmetic for moduli below 2^57 -------------------------------------------------------------
+// floor(x*ws / 2^64) computed from three 32x32 products (the lo*lo partial product and one carry are dropped):
+// the estimate is low by at most 2, so the Shoup product below lands in [0, 4q) instead of [0, 2q). With q < 2^57
+// a 14-stage transform can let values grow by 4q per stage (< 60q < 2^64) and skip every conditional subtraction.
+HD u64 mulhi_approx(u64 x, u64 ws) {
+  const u32 xl = static_cast<u32>(x), xh = static_cast<u32>(x >> 32);
+  const u32 wl = static_cast<u32>(ws), wh = static_cast<u32>(ws >> 32);
+#if defined(__CUDA_ARCH__)
+  const u32 c1 = __umulhi(xl, wh), c2 = __umulhi(xh, wl);
+#else
+  const u32 c1 = static_cast<u32>((static_cast<u64>(xl) * wh) >> 32), c2 = static_cast<u32>((static_cast<u64>(xh) * wl) >> 32);
+#endif
+  return static_cast<u64>(xh) * wh + c1 + c2;
+}
+// x * w mod q up to a multiple of q: result in [0, 4q) for any 64-bit x. nq = 2^64 - q.
+HD u64 mul_shoup_wide(u64 x, u64 w, u64 ws, u64 nq) { return x * w + mulhi_approx(x, ws) * nq; }
+constexpr u64 kWideSlackLimit = 1ULL << 57;
+
 HD u64 add_mod(u64 a, u64 b, u64 q) {
   u64 s = a + b;
   return s >= q ? s - q : s;
