@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference's interface for the hot path (Python flavour; the C++ flavour is
+host/hhe_seal_shim.h). Same names, argument meaning and error behaviour as
+
+    pasta::PASTA_SEAL            src/pasta/pasta_3_seal.h:9-54      (decomposition, HE_decrypt, activate_bsgs)
+    pasta::SEALZpCipher          src/pasta/SEAL_Cipher.h:79,87-88   (mask, flatten)
+    sealhelper::*                src/util/sealhelper.h:84-87,125-129 (packed_enc_multiply, encrypted_vec_sum)
+    BaseCSP::decompose / CSP_hhe_pktnn_1fc::evaluateModel  src/examples/CSP/CSP.cpp:235-323
+
+Ciphertexts are numpy uint64 arrays in SEAL's layout ([size][L][N]); keys are raw KSwitchKeys arrays.
+"""
+import numpy as np
+
+from . import KEYSET_0, KEYSET_1, RELIN, Context, HheInvalidArgument  # noqa: F401
+
+PASTA_T = 128
+NONCE = 123456789
+
+
+class PASTA_SEAL:
+    """pasta::PASTA_SEAL. `relin_key` and `galois_keys` ({galois_elt: ksk}) play the role of the rk/gk constructor copies."""
+
+    def __init__(self, context: Context, relin_key=None, galois_keys=None):
+        self.ctx = context
+        self.use_bsgs = False
+        self.secret_key_encrypted = None
+        if relin_key is not None:
+            context.load_ksk(RELIN, 0, relin_key)
+        for elt, k in (galois_keys or {}).items():
+            context.load_ksk(KEYSET_0, elt, k)
+
+    def get_cipher_name(self):
+        return "PASTA-SEAL (n=128,r=3) [B200]"
+
+    def get_plain_size(self):
+        return PASTA_T
+
+    def activate_bsgs(self, activate):
+        self.use_bsgs = bool(activate)
+
+    def add_gk_indices(self):
+        """pasta_3_seal.cpp:190-201"""
+        idx = [0, -1]
+        if 2 * PASTA_T != self.ctx.N:
+            idx.append(PASTA_T)
+        if self.use_bsgs:
+            idx += [-16 * k for k in range(1, 8)]
+        return idx
+
+    def decomposition(self, ciphertext, enc_ssk, batch_encoder=False):
+        """pasta_3_seal.cpp:106-172: counters restart at 0 for every call; `batch_encoder` is ignored as in the reference."""
+        key = enc_ssk[0] if isinstance(enc_ssk, (list, tuple)) else enc_ssk
+        return self.ctx.pasta3_decompose(key, ciphertext, use_bsgs=self.use_bsgs, nonce=NONCE, first_counter=0)
+
+    def HE_decrypt(self, ciphertext, batch_encoder=False):
+        """pasta_3_seal.cpp:42-104 (the member key must have been set, as encrypt_key does in the reference)."""
+        if self.secret_key_encrypted is None:
+            raise HheInvalidArgument(-1, "secret_key_encrypted is not set")
+        return self.decomposition(ciphertext, self.secret_key_encrypted)
+
+    def mask(self, cipher, mask):
+        return self.ctx.mask(cipher, mask)
+
+    def flatten(self, cts, galois_keys=None):
+        """SEAL_Cipher.cpp:170-181. `galois_keys` ({elt: ksk}) are uploaded as keyset 1, like the dedicated csp_gk."""
+        if galois_keys:
+            for elt, k in galois_keys.items():
+                self.ctx.load_ksk(KEYSET_1, elt, k)
+            return self.ctx.flatten(cts, keys=KEYSET_1)
+        return self.ctx.flatten(cts, keys=KEYSET_0)
+
+
+def packed_enc_multiply(ctx: Context, encrypted1, encrypted2):
+    """sealhelper::packed_enc_multiply (src/util/sealhelper.cpp:268-274) -> size-3 ciphertext"""
+    return ctx.multiply(encrypted1, encrypted2)
+
+
+def encrypted_vec_sum(ctx: Context, encrypted_inp, vec_size, keyset=KEYSET_1):
+    """sealhelper::encrypted_vec_sum (src/util/sealhelper.cpp:379-392); the total lands in slot vec_size-1"""
+    return ctx.vec_sum(encrypted_inp, vec_size, keys=keyset)
+
+
+def decompose(hhe: PASTA_SEAL, records, enc_sym_key, input_len, flatten_keys=None, mask_in_place=True):
+    """BaseCSP::decompose (CSP.cpp:235-283) for a list of symmetric-ciphertext records. `mask_in_place=False`
+    reproduces the service's mask-on-a-copy quirk; the monolithic demos mask in place."""
+    out = []
+    rem = input_len % PASTA_T
+    for rec in records:
+        blocks = hhe.decomposition(np.asarray(rec, dtype=np.uint64), enc_sym_key, True)
+        if rem and mask_in_place:
+            blocks[-1] = hhe.mask(blocks[-1], np.ones(rem, dtype=np.uint64))
+        out.append(hhe.flatten(blocks, flatten_keys) if len(blocks) > 1 else blocks[0])
+    return out
+
+
+def evaluate_model(ctx: Context, decomposed, enc_weights, input_len, keyset=KEYSET_1):
+    """CSP_hhe_pktnn_1fc::evaluateModel (CSP.cpp:288-323) generalised to several weight rows
+    (hhe_pktnn_examples.cpp:957-992): out[sample][row] = vec_sum(relin(x * w_row), input_len)."""
+    return ctx.fc_rows(np.stack(decomposed), enc_weights, input_len, keys=keyset)

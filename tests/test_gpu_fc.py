@@ -1,0 +1,84 @@
+"""Encrypted FC layer at full size on the B200 (BASELINE.json configs[1]/[2] shapes), written like the reference's
+monolithic demos (src/examples/hhe_pktnn_examples.cpp:385-711, 713-1010): transcipher -> mask -> flatten ->
+packed_enc_multiply -> relinearize -> encrypted_vec_sum with the analyst's default Galois keys -> decrypt slot n-1 ->
+compare with the plaintext dot product / class prediction. Inputs are synthetic (the MNIST / MIT-BIH inputs are missing
+from the reference checkout); weights are synthetic integers in the trained range."""
+import importlib
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+from oracle import refshim as R
+
+pkg = common.package()
+host = importlib.import_module(common.PKG + ".host")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not R.available(), reason="oracle/_ref/libhhe_ref.so not built")]
+N, T = 16384, common.T
+
+
+def signed(v):
+    v = int(v)
+    return v - T if v > T // 2 else v
+
+
+@pytest.fixture(scope="module")
+def world():
+    steps = (0, -1, 128) + tuple(-128 * i for i in range(1, 7))
+    ref = R.Ref(N, T, None, seed=21, steps=steps, default_gk=True)
+    ctx = pkg.Context(N, T, ref.q, device=0)
+    common.load_keys_from_ref(ctx, ref, keysets=(0, 1))
+    rng = np.random.default_rng(8)
+    key = rng.integers(0, T, 256, dtype=np.uint64)
+    hhe = host.PASTA_SEAL(ctx)
+    yield dict(ref=ref, ctx=ctx, hhe=hhe, rng=rng, key=key, enc_key=ref.encrypt(common.pack_key(key, N)))
+    ctx.close()
+    ref.close()
+
+
+def test_ecg_row_bit_exact_with_seal(world):
+    """configs[2] shape (128 -> 1): one sample, compared limb for limb with the reference (13.7 s of SEAL on one core)."""
+    ref, ctx, hhe, rng = world["ref"], world["ctx"], world["hhe"], world["rng"]
+    x = rng.integers(0, 256, 128, dtype=np.uint64)
+    w = rng.integers(-128, 128, 128)
+    sym = O.pasta_plain(world["key"], T, x)
+    c = hhe.decomposition(sym, [world["enc_key"]], True)[0]
+    enc_w = ref.encrypt(np.mod(w, T).astype(np.uint64))
+    prod = host.packed_enc_multiply(ctx, c, enc_w)
+    assert np.array_equal(prod, ref.multiply(c, enc_w))
+    lin = ctx.relinearize(prod)
+    assert np.array_equal(lin, ref.relinearize(prod))
+    got = host.encrypted_vec_sum(ctx, lin, 128)
+    assert np.array_equal(got, ref.vec_sum(lin, 128, 1))
+    slots, budget = ref.decrypt(got)
+    assert budget > 0 and signed(slots[127]) == int(np.dot(x.astype(np.int64), w)) % T - (T if int(np.dot(x.astype(np.int64), w)) % T > T // 2 else 0)
+
+
+def test_mnist_sample_prediction(world):
+    """configs[1] shape (784 -> 10): 7 blocks, mask(16 ones) on the last, flatten, 10 encrypted weight rows."""
+    ref, ctx, hhe, rng = world["ref"], world["ctx"], world["hhe"], world["rng"]
+    x = rng.integers(0, 256, 784, dtype=np.uint64)
+    W = rng.integers(-8, 9, (10, 784))
+    sym = O.pasta_plain(world["key"], T, x)
+    flat = host.decompose(hhe, [sym], [world["enc_key"]], 784)[0]
+    slots, _ = ref.decrypt(flat)
+    assert np.array_equal(slots[:784], x) and not slots[784:8192].any()
+    enc_w = np.stack([ref.encrypt(np.mod(W[r], T).astype(np.uint64)) for r in range(10)])
+    out = host.evaluate_model(ctx, [flat], enc_w, 784)[0]
+    logits = [signed(ref.decrypt(out[r])[0][783]) for r in range(10)]
+    want = [int(v) for v in W @ x.astype(np.int64)]
+    assert [v % T for v in logits] == [v % T for v in want]
+    if max(abs(v) for v in want) < T // 2:
+        assert int(np.argmax(logits)) == int(np.argmax(want))
+    # one output neuron limb-exact against the reference's own op sequence would take ~100 s of SEAL: check the
+    # first 40 rotations' partial sum instead (same NAF chains, same keys)
+    lin = ctx.relinearize(ctx.multiply(flat, enc_w[0]))
+    assert np.array_equal(ctx.vec_sum(lin, 40), ref.vec_sum(lin, 40, 1))
+
+
+def test_missing_default_key_raises_like_seal(world):
+    ctx = world["ctx"]
+    c = world["enc_key"]
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.vec_sum(c, 5, keys=0)  # keyset 0 has no power-of-two keys: NAF(-2) = single term without a key
