@@ -61,7 +61,8 @@ const char *hhe_version(void);
  * device: CUDA ordinal. stream: a cudaStream_t to run on (NULL: the context creates its own). */
 int hhe_ctx_create(hhe_ctx **out, uint64_t N, uint64_t t, const uint64_t *q, int nq, int device, void *stream);
 void hhe_ctx_destroy(hhe_ctx *ctx);
-/* info[0..6) = N, L, K, t, max batch (blocks processed per launch wave), SM count */
+/* info[0..7) = N, L, K, t, max batch (blocks processed per lock-step wave), SM count,
+ * number of moduli served by the FP64-pipe kernels (q <= 2^49; the others use the integer Shoup kernels) */
 int hhe_ctx_info(const hhe_ctx *ctx, uint64_t *info);
 void *hhe_ctx_stream(const hhe_ctx *ctx);
 /* Blocks per lock-step batch inside decompose (0 = automatic from free HBM). */

@@ -39,7 +39,7 @@ int main(int argc, char **argv) {
   for (size_t i = 1; i < blocks; i++) flat_steps.push_back(-(int)(i * 128));
   if (!flat_steps.empty()) keygen.create_galois_keys(flat_steps, flat_gk);
   std::vector<int> pow2;
-  for (int s = 1; s < (int)sum_len; s <<= 1) pow2.push_back(-s), pow2.push_back(s);  // NAF terms have both signs
+  for (int s = 1; s <= (int)sum_len; s <<= 1) pow2.push_back(-s), pow2.push_back(s);  // NAF terms have both signs
   keygen.create_galois_keys(pow2, sum_gk);
   BatchEncoder benc(*context);
   Encryptor enc(*context, pk);

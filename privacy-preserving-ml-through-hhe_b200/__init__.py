@@ -117,9 +117,10 @@ class Context:
             pass
 
     def info(self):
-        out = np.zeros(6, dtype=np.uint64)
+        out = np.zeros(7, dtype=np.uint64)
         self._chk(self.lib.hhe_ctx_info(self.h, out.ctypes.data_as(_u64p)))
-        return dict(N=int(out[0]), L=int(out[1]), K=int(out[2]), t=int(out[3]), batch=int(out[4]), sms=int(out[5]))
+        return dict(N=int(out[0]), L=int(out[1]), K=int(out[2]), t=int(out[3]), batch=int(out[4]), sms=int(out[5]),
+                    fp64_moduli=int(out[6]))
 
     def stream(self):
         return self.lib.hhe_ctx_stream(self.h)

@@ -85,6 +85,8 @@ int hhe_ctx_info(const hhe_ctx *ctx, uint64_t *info) {
     info[3] = e.params().t;
     info[4] = e.batch_limit();
     info[5] = e.dev().sm_count;
+    info[6] = 0;
+    for (int i = 0; i < 2 * e.params().K; ++i) info[6] += table_is_f64(e.params(), i) ? 1 : 0;
   });
 }
 

@@ -1,6 +1,7 @@
 // Per-context constant block, copied once to HBM and read (broadcast, L1/L2-resident) by every kernel.
 #pragma once
 #include "modarith.h"
+#include "modarith_f64.h"
 #include "params.h"
 
 namespace hhe {
@@ -14,6 +15,10 @@ struct DevConsts {
   u64 t, half_t, q_mod_t;
   DevMod mod[kMaxTab];  // by NTT table id: [0,K) q_i, [K,2K) Bsk, [2K] t
   W2 n_inv[kMaxTab];    // N^-1 per table
+  // FP64-pipe path (modarith_f64.h): tables whose modulus is <= 2^49 keep twiddles / keys as (w, w/q) doubles
+  unsigned char f64[kMaxTab];
+  double qf[kMaxTab], qinvf[kMaxTab];
+  D2 n_inv_f[kMaxTab];
   u64 q_div_t_mod_q[kMaxLimbs];
   u64 half_sp;
   u64 half_sp_mod_q[kMaxLimbs];
@@ -50,6 +55,17 @@ inline DevMod make_devmod(u64 q) {
 
 inline W2 w2(const Twiddle &t) { return W2{t.w, t.ws}; }
 
+// The FP64 path needs 8q <= 2^52 and at most 8 key digits (the key inner product sums L terms of magnitude <= q).
+// The plaintext table (q = t) stays on the integer path: its values feed integer-only kernels.
+inline bool table_is_f64(const Params &p, int tab) {
+#ifdef HHE_NO_F64
+  (void)p; (void)tab;
+  return false;
+#else
+  return tab < 2 * p.K && p.tab[tab].q != 0 && p.tab[tab].q <= kF64ModLimit && p.L <= 8;
+#endif
+}
+
 inline DevConsts make_devconsts(const Params &p) {
   DevConsts c{};
   c.N = p.N;
@@ -63,6 +79,10 @@ inline DevConsts make_devconsts(const Params &p) {
     if (!p.tab[i].q) continue;
     c.mod[i] = make_devmod(p.tab[i].q);
     c.n_inv[i] = w2(p.tab[i].n_inv);
+    c.f64[i] = table_is_f64(p, static_cast<int>(i)) ? 1 : 0;
+    c.qf[i] = static_cast<double>(p.tab[i].q);
+    c.qinvf[i] = 1.0 / static_cast<double>(p.tab[i].q);
+    c.n_inv_f[i] = D2{static_cast<double>(p.tab[i].n_inv.w), static_cast<double>(p.tab[i].n_inv.w) / static_cast<double>(p.tab[i].q)};
   }
   c.half_sp = p.half_sp;
   for (int i = 0; i < kMaxLimbs; ++i) {

@@ -78,9 +78,17 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   std::vector<W2> tw(ntab * 2 * P_.N);
   for (size_t t = 0; t < ntab; ++t) {
     if (!P_.tab[t].q) continue;
+    const bool f64 = table_is_f64(P_, static_cast<int>(t));
+    const double qd = static_cast<double>(P_.tab[t].q);
     for (u64 k = 0; k < P_.N; ++k) {
-      tw[(t * 2) * P_.N + k] = w2(P_.tab[t].fwd[k]);
-      tw[(t * 2 + 1) * P_.N + k] = w2(P_.tab[t].inv[k]);
+      if (f64) {  // FP64-pipe tables: {w, w/q} as doubles in the same 16-byte slots
+        const double wf = static_cast<double>(P_.tab[t].fwd[k].w), wi = static_cast<double>(P_.tab[t].inv[k].w);
+        tw[(t * 2) * P_.N + k] = W2{double_to_bits(wf), double_to_bits(wf / qd)};
+        tw[(t * 2 + 1) * P_.N + k] = W2{double_to_bits(wi), double_to_bits(wi / qd)};
+      } else {
+        tw[(t * 2) * P_.N + k] = w2(P_.tab[t].fwd[k]);
+        tw[(t * 2 + 1) * P_.N + k] = w2(P_.tab[t].inv[k]);
+      }
     }
   }
   dTw_ = static_cast<W2 *>(dev_.dmalloc(tw.size() * sizeof(W2)));

@@ -12,6 +12,9 @@ struct TwRef {
   u64 N;
   HD const W2 *fwd(int tab) const { return base + (static_cast<size_t>(tab) * 2) * N; }
   HD const W2 *inv(int tab) const { return base + (static_cast<size_t>(tab) * 2 + 1) * N; }
+  // FP64 tables hold D2 {w, w/q} in the same 16-byte slots
+  HD const D2 *fwd_f(int tab) const { return reinterpret_cast<const D2 *>(fwd(tab)); }
+  HD const D2 *inv_f(int tab) const { return reinterpret_cast<const D2 *>(inv(tab)); }
 };
 
 struct TabMap {  // limb index inside an item -> NTT table id
@@ -38,6 +41,27 @@ struct NttBody {
     const u64 q = C->mod[tab].q;
     const u64 *src = in + static_cast<size_t>(bid) * S;
     u64 *dst = out + static_cast<size_t>(bid) * S;
+    if (C->f64[tab]) {  // FP64-pipe transform (modarith_f64.h)
+      double *fm = reinterpret_cast<double *>(smem);
+      const double qd = C->qf[tab], qi = C->qinvf[tab];
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(src[i]);
+      }
+      SYNC();
+      if (!inverse) {
+        ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(tab), qd, qi, 1, nt, 1.0f);
+        FOR_THREADS(tid, nt) {
+          for (int i = tid; i < S; i += nt) dst[i] = f_canonical(fm[pidx(i)], qd, qi);
+        }
+      } else {
+        ntt_inv_core_f64<LOGS>(fm, tw.inv_f(tab), qd, qi, 1, nt);
+        const D2 ninv = C->n_inv_f[tab];
+        FOR_THREADS(tid, nt) {
+          for (int i = tid; i < S; i += nt) dst[i] = f_canonical(f_mulmod_const(fm[pidx(i)], ninv, qd), qd, qi);
+        }
+      }
+      return;
+    }
     FOR_THREADS(tid, nt) {
       for (int i = tid; i < S; i += nt) sm[pidx(i)] = src[i];
     }
@@ -75,6 +99,71 @@ struct KsDigitsBody {
   const DevConsts *C;
   TwRef tw;
   int count;
+  // FP64-pipe version of the same computation (q_k <= 2^49): digits, twiddles, key and accumulators are doubles.
+  HD void run_f64(int b, int k, int h, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH;
+    const int N = 2 * S;
+    const int K = C->K, L = C->L;
+    double *fm = reinterpret_cast<double *>(smem);
+    double *acc0 = fm + ntt_smem_words(S);
+    double *acc1 = acc0 + S;
+    const double q = C->qf[k], qi = C->qinvf[k];
+    const D2 *twk = tw.fwd_f(k);
+    const D2 w1 = twk[1];
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) acc0[i] = acc1[i] = 0.0;
+    }
+    for (int J = 0; J < L; ++J) {
+      const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
+      const bool reduce = C->mod[J].q > C->mod[k].q;
+      FOR_THREADS(tid, nt) {
+        constexpr int U = 4;
+        for (int i0 = tid; i0 < S; i0 += nt * U) {
+          u64 xs[U], ys[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nt;
+            xs[u] = i < S ? dig[i] : 0;
+            ys[u] = i < S ? dig[i + S] : 0;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * nt;
+            if (i < S) {
+              double x = u_to_f(xs[u]), y = u_to_f(ys[u]);  // digits are < q_J < 2^52
+              if (reduce) {
+                x = f_reduce(x, q, qi);
+                y = f_reduce(y, q, qi);
+              }
+              const double t = f_mulmod_const(y, w1, q);
+              fm[pidx(i)] = h ? f_add(x, -t) : f_add(x, t);  // |.| <= 2q
+            }
+          }
+        }
+      }
+      SYNC();
+      ntt_fwd_core_f64<LOGH>(fm, twk, q, qi, 2 + h, nt, 2.0f);
+      const D2 *k0 = reinterpret_cast<const D2 *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+      const D2 *k1 = k0 + static_cast<size_t>(K) * N;
+      FOR_THREADS(tid, nt) {
+#pragma unroll 4
+        for (int i = tid; i < S; i += nt) {
+          const double v = fm[pidx(i)];
+          acc0[i] = f_add(acc0[i], f_mulmod_const(v, k0[i], q));  // L <= 8 terms of magnitude <= q: exact
+          acc1[i] = f_add(acc1[i], f_mulmod_const(v, k1[i], q));
+        }
+      }
+      SYNC();
+    }
+    u64 *o0 = acc + ((static_cast<size_t>(b) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+    u64 *o1 = o0 + static_cast<size_t>(K) * N;
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) {
+        o0[i] = f_canonical(acc0[i], q, qi);
+        o1[i] = f_canonical(acc1[i], q, qi);
+      }
+    }
+  }
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGH;
     const int N = 2 * S;
@@ -87,6 +176,10 @@ struct KsDigitsBody {
     u64 *sm = reinterpret_cast<u64 *>(smem);
     u64 *acc0 = sm + ntt_smem_words(S);
     u64 *acc1 = acc0 + S;
+    if (C->f64[k]) {
+      run_f64(b, k, h, nt, smem);
+      return;
+    }
     const DevMod mk = C->mod[k];
     const u64 q = mk.q, two_q = q << 1, nq = 0 - q, four_q = q << 2;
     const bool wide = q < kWideSlackLimit;
@@ -409,6 +502,23 @@ struct LiftNttBody {
     const size_t item = bid / L;
     const u64 q = C->mod[i].q, inc = q - C->t, thr = C->half_t;
     const u64 *src = pt + item * S;
+    if (C->f64[i]) {
+      double *fm = reinterpret_cast<double *>(smem);
+      const double qd = C->qf[i], qi = C->qinvf[i];
+      FOR_THREADS(tid, nt) {
+        for (int j = tid; j < S; j += nt) {
+          const u64 m = src[j];
+          fm[pidx(j)] = u_to_f(m >= thr ? m + inc : m);
+        }
+      }
+      SYNC();
+      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 1, nt, 1.0f);
+      u64 *dstf = out + static_cast<size_t>(bid) * S;
+      FOR_THREADS(tid, nt) {
+        for (int j = tid; j < S; j += nt) dstf[j] = f_canonical(fm[pidx(j)], qd, qi);
+      }
+      return;
+    }
     FOR_THREADS(tid, nt) {
       for (int j = tid; j < S; j += nt) {
         const u64 m = src[j];
@@ -447,13 +557,30 @@ struct NttMacBody {
     const DevMod mi = C->mod[i];
     const u64 q = mi.q;
     const u64 *src = ct + static_cast<size_t>(bid) * S;
+    const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
+    u64 *dst = sum + static_cast<size_t>(bid) * S;
+    if (C->f64[i]) {
+      double *fm = reinterpret_cast<double *>(smem);
+      const double qd = C->qf[i], qi = C->qinvf[i];
+      FOR_THREADS(tid, nt) {
+        for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
+      }
+      SYNC();
+      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 1, nt, 1.0f);
+      FOR_THREADS(tid, nt) {
+        for (int j = tid; j < S; j += nt) {
+          u64 v = f_canonical(f_mulmod_var(fm[pidx(j)], u_to_f(d[j]), qd, qi), qd, qi);
+          if (!first) v = add_mod(v, dst[j], q);
+          dst[j] = v;
+        }
+      }
+      return;
+    }
     FOR_THREADS(tid, nt) {
       for (int j = tid; j < S; j += nt) sm[pidx(j)] = src[j];
     }
     SYNC();
     ntt_fwd_core<LOGS>(sm, tw.fwd(i), q, 1, nt);
-    const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
-    u64 *dst = sum + static_cast<size_t>(bid) * S;
     FOR_THREADS(tid, nt) {
       for (int j = tid; j < S; j += nt) {
         u64 v = mul_mod(sm[pidx(j)], d[j], mi);
@@ -586,8 +713,14 @@ struct ShoupifyBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const DevMod m = C->mod[(g / N) % C->K];
+        const int limb = static_cast<int>((g / N) % C->K);
+        const DevMod m = C->mod[limb];
         const u64 w = in[g];
+        if (C->f64[limb]) {  // FP64 limbs keep the key as (k, k/q) doubles in the same 16-byte slot
+          const double wd = u_to_f(w);
+          const D2 dv{wd, wd / C->qf[limb]};
+          reinterpret_cast<D2 *>(out)[g] = dv;
+        } else {
         // floor(w * 2^64 / q): Barrett estimate from floor(2^128/q), then exact correction
         u64 est = mulhi64(w, m.cr0) + w * m.cr1;
         // remainder check: w*2^64 - est*q must be in [0, q)
@@ -597,6 +730,7 @@ struct ShoupifyBody {
           ++est;
         }
         out[g] = W2{w, est};
+        }
       }
     }
   }

@@ -13,6 +13,7 @@
 // stages the N/S contiguous chunks are independent; `mc` = (N/S) + chunk selects the twiddle rows of that chunk.
 #pragma once
 #include "modarith.h"
+#include "modarith_f64.h"
 
 namespace hhe {
 
@@ -157,6 +158,124 @@ HD void ntt_inv_core(u64 *sm, const W2 *__restrict__ tw, u64 q, u32 mc, int nt) 
   }
   FOR_THREADS(tid, nt) {
     for (int g = tid; g < (1 << (LOGS - R0)); g += nt) inv_group<R0>(sm, tw, q, LOGS, 0, mc, g);
+  }
+  SYNC();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP64-pipe variants (q <= 2^49, see modarith_f64.h). Shared memory holds doubles (signed integers, |x| < 8q).
+// Bound bookkeeping is in units of q: a forward stage adds at most 1 (|w*b mod q| <= q), an inverse stage doubles.
+
+template <int R>
+HD void fwd_group_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, int logS, int s0, u32 mc, int g, bool reduce) {
+  constexpr int E = 1 << R;
+  const int lg = logS - s0 - R;
+  const int lo = g & ((1 << lg) - 1), hi = g >> lg;
+  const int base = (hi << (logS - s0)) + lo;
+  D2 wv[E];
+#pragma unroll
+  for (int d = 0; d < R; ++d) {
+    const u32 tb = (mc << (s0 + d)) + (static_cast<u32>(hi) << d);
+#pragma unroll
+    for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw[tb + j];
+  }
+  double x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = sm[pidx(base + (e << lg))];
+  if (reduce) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = f_reduce(x[e], q, qinv);
+  }
+#pragma unroll
+  for (int d = 0; d < R; ++d) {
+    const int half = E >> (d + 1);
+#pragma unroll
+    for (int j = 0; j < (1 << d); ++j) {
+      const D2 w = wv[(1 << d) + j];
+#pragma unroll
+      for (int k = 0; k < half; ++k) {
+        double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
+        const double t = f_mulmod_const(b, w, q);
+        b = f_add(a, -t);
+        a = f_add(a, t);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) sm[pidx(base + (e << lg))] = x[e];
+}
+
+template <int R>
+HD void inv_group_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, int logS, int s0, u32 mc, int g) {
+  constexpr int E = 1 << R;
+  const int lg = logS - s0 - R;
+  const int lo = g & ((1 << lg) - 1), hi = g >> lg;
+  const int base = (hi << (logS - s0)) + lo;
+  D2 wv[E];
+#pragma unroll
+  for (int d = 0; d < R; ++d) {
+    const u32 tb = (mc << (s0 + d)) + (static_cast<u32>(hi) << d);
+#pragma unroll
+    for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw[tb + j];
+  }
+  double x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = f_reduce(sm[pidx(base + (e << lg))], q, qinv);  // |x| <= q/2: R <= 3 doublings stay < 8q
+#pragma unroll
+  for (int d = R - 1; d >= 0; --d) {
+    const int half = E >> (d + 1);
+#pragma unroll
+    for (int j = 0; j < (1 << d); ++j) {
+      const D2 w = wv[(1 << d) + j];
+#pragma unroll
+      for (int k = 0; k < half; ++k) {
+        double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
+        const double dlt = f_add(a, -b);
+        a = f_add(a, b);
+        b = f_mulmod_const(dlt, w, q);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) sm[pidx(base + (e << lg))] = x[e];
+}
+
+// Forward transform on doubles. bound_in: |input| <= bound_in * q (1 for canonical residues). Output: |x| <= 7.5 q.
+template <int LOGS>
+HD void ntt_fwd_core_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, u32 mc, int nt, float bound_in) {
+  constexpr int R0 = NttSchedule<LOGS>::kFirst;
+  static_assert(kRadixLog <= 3, "FP64 bound schedule assumes at most 3 stages per register pass");
+  float bound = bound_in;
+  {
+    const bool red = bound + R0 > 7.5f;
+    FOR_THREADS(tid, nt) {
+      for (int g = tid; g < (1 << (LOGS - R0)); g += nt) fwd_group_f64<R0>(sm, tw, q, qinv, LOGS, 0, mc, g, red);
+    }
+    SYNC();
+    bound = (red ? 0.5f : bound) + R0;
+  }
+  for (int s0 = R0; s0 < LOGS; s0 += kRadixLog) {
+    const bool red = bound + kRadixLog > 7.5f;
+    FOR_THREADS(tid, nt) {
+      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) fwd_group_f64<kRadixLog>(sm, tw, q, qinv, LOGS, s0, mc, g, red);
+    }
+    SYNC();
+    bound = (red ? 0.5f : bound) + kRadixLog;
+  }
+}
+
+// Inverse transform on doubles (without 1/N). Any |input| < 8q. Output: |x| <= 4q.
+template <int LOGS>
+HD void ntt_inv_core_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, u32 mc, int nt) {
+  constexpr int R0 = NttSchedule<LOGS>::kFirst;
+  for (int s0 = LOGS - kRadixLog; s0 >= R0; s0 -= kRadixLog) {
+    FOR_THREADS(tid, nt) {
+      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) inv_group_f64<kRadixLog>(sm, tw, q, qinv, LOGS, s0, mc, g);
+    }
+    SYNC();
+  }
+  FOR_THREADS(tid, nt) {
+    for (int g = tid; g < (1 << (LOGS - R0)); g += nt) inv_group_f64<R0>(sm, tw, q, qinv, LOGS, 0, mc, g);
   }
   SYNC();
 }

@@ -54,9 +54,10 @@ def ntt_primes(N, bits, count):
     return out
 
 
-def small_params(N=1024, data_primes=6):
-    """A test ring: `data_primes` 50-bit primes + one 51-bit special prime (enough noise room for PASTA-3 at t=65537)."""
-    return ntt_primes(N, 50, data_primes) + ntt_primes(N, 51, 1)
+def small_params(N=1024, data_primes=6, bits=50):
+    """A test ring: `data_primes` primes of `bits` bits + one special prime one bit larger.
+    bits=50 exercises the integer (Shoup) kernels; bits=48 (all moduli <= 2^49) the FP64-pipe kernels."""
+    return ntt_primes(N, bits, data_primes) + ntt_primes(N, bits + 1, 1)
 
 
 def package():

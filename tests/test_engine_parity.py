@@ -90,9 +90,10 @@ class ToyKeys:
         return orc.add_plain(ct, pt)
 
 
-@pytest.fixture(scope="module")
-def world():
-    q = common.small_params(N, 6)
+# two rings: 50/51-bit primes -> integer Shoup kernels; 48/49-bit primes -> FP64-pipe kernels (the BFVDefault(16384) case)
+@pytest.fixture(scope="module", params=["int50", "f64_48"])
+def world(request):
+    q = common.small_params(N, 6, 50) if request.param == "int50" else common.small_params(N, 7, 48)
     orc = O.Oracle(N, common.T, q)
     keys = ToyKeys(orc, 42)
     steps0 = (0, -1, 128) + BSGS_STEPS
