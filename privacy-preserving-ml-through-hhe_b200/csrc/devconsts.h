@@ -55,14 +55,18 @@ inline DevMod make_devmod(u64 q) {
 
 inline W2 w2(const Twiddle &t) { return W2{t.w, t.ws}; }
 
-// The FP64 path needs 8q <= 2^52 and at most 8 key digits (the key inner product sums L terms of magnitude <= q).
-// The plaintext table (q = t) stays on the integer path: its values feed integer-only kernels.
+// The FP64 path needs 8q <= 2^52 for EVERY coefficient prime (key-switching keys are then stored as doubles) and at
+// most 8 key digits (the key inner product sums L terms of magnitude <= 1.5q in a double). The BEHZ auxiliary primes
+// (61 bit) and the plaintext table (q = t, whose values feed integer-only kernels) stay on the integer path.
 inline bool table_is_f64(const Params &p, int tab) {
 #ifdef HHE_NO_F64
   (void)p; (void)tab;
   return false;
 #else
-  return tab < 2 * p.K && p.tab[tab].q != 0 && p.tab[tab].q <= kF64ModLimit && p.L <= 8;
+  if (tab >= p.K || p.L > 8) return false;
+  for (int i = 0; i < p.K; ++i)
+    if (p.q[i] > kF64ModLimit) return false;
+  return true;
 #endif
 }
 

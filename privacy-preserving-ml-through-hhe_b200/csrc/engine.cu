@@ -75,20 +75,33 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   dC_ = static_cast<DevConsts *>(dev_.dmalloc(sizeof(DevConsts)));
   dev_.h2d(dC_, &hc, sizeof(DevConsts));
   const size_t ntab = P_.tab.size();
+  f64_gmin_ = P_.logn % 3 ? P_.logn % 3 : 3;
+  compact_keys_ = true;
+  for (int k = 0; k < P_.K; ++k) compact_keys_ = compact_keys_ && table_is_f64(P_, k);
   std::vector<W2> tw(ntab * 2 * P_.N);
   for (size_t t = 0; t < ntab; ++t) {
     if (!P_.tab[t].q) continue;
     const bool f64 = table_is_f64(P_, static_cast<int>(t));
-    const double qd = static_cast<double>(P_.tab[t].q);
-    for (u64 k = 0; k < P_.N; ++k) {
-      if (f64) {  // FP64-pipe tables: {w, w/q} as doubles in the same 16-byte slots
-        const double wf = static_cast<double>(P_.tab[t].fwd[k].w), wi = static_cast<double>(P_.tab[t].inv[k].w);
-        tw[(t * 2) * P_.N + k] = W2{double_to_bits(wf), double_to_bits(wf / qd)};
-        tw[(t * 2 + 1) * P_.N + k] = W2{double_to_bits(wi), double_to_bits(wi / qd)};
-      } else {
-        tw[(t * 2) * P_.N + k] = w2(P_.tab[t].fwd[k]);
-        tw[(t * 2 + 1) * P_.N + k] = w2(P_.tab[t].inv[k]);
+    if (f64) {
+      // FP64-pipe tables: two planes of N doubles per direction (index-major, component-major; see ntt_core.h)
+      for (int dir = 0; dir < 2; ++dir) {
+        double *plane = reinterpret_cast<double *>(&tw[(t * 2 + dir) * P_.N]);
+        const std::vector<Twiddle> &src = dir ? P_.tab[t].inv : P_.tab[t].fwd;
+        for (u64 k = 0; k < P_.N; ++k) plane[k] = static_cast<double>(src[k].w);
+        double *cm = plane + P_.N;
+        for (int g0 = f64_gmin_; g0 + 3 <= P_.logn; g0 += 3) {
+          double *T = cm + f64tw_offset(g0, f64_gmin_);
+          for (int d = 0; d < 3; ++d)
+            for (int j = 0; j < (1 << d); ++j)
+              for (u64 H = 0; H < (1ULL << g0); ++H)
+                T[(static_cast<size_t>((1 << d) - 1 + j) << g0) + H] = static_cast<double>(src[(1ULL << (g0 + d)) + (H << d) + j].w);
+        }
       }
+      continue;
+    }
+    for (u64 k = 0; k < P_.N; ++k) {
+      tw[(t * 2) * P_.N + k] = w2(P_.tab[t].fwd[k]);
+      tw[(t * 2 + 1) * P_.N + k] = w2(P_.tab[t].inv[k]);
     }
   }
   dTw_ = static_cast<W2 *>(dev_.dmalloc(tw.size() * sizeof(W2)));
@@ -153,8 +166,8 @@ void Engine::load_ksk(int kind, u32 elt, const u64 *host_ksk) {
   Scope sc(*this);
   u64 *raw = scratch(words);
   dev_.h2d(raw, host_ksk, words * 8);
-  W2 *dst = static_cast<W2 *>(dev_.dmalloc(words * sizeof(W2)));
-  ShoupifyBody body{raw, dst, dC_, words};
+  W2 *dst = static_cast<W2 *>(dev_.dmalloc(words * (compact_keys_ ? sizeof(double) : sizeof(W2))));
+  ShoupifyBody body{raw, dst, dC_, words, compact_keys_ ? 1 : 0};
   dev_.launch(body, ew_grid(words), kEwThreads, 0);
   dev_.sync();  // host_ksk may be released by the caller; raw scratch is recycled
   auto key = std::make_pair(kind, elt);

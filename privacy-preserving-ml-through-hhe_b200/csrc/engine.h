@@ -72,7 +72,7 @@ class Engine {
   void vec_sum(const u64 *a, size_t n, int keyset, u64 *out, size_t items);
 
   const DevConsts *dconsts() const { return dC_; }
-  TwRef twref() const { return TwRef{dTw_, P_.N}; }
+  TwRef twref() const { return TwRef{dTw_, P_.N, f64_gmin_}; }
   const u32 *index_map() const { return dIndex_; }
 
  private:
@@ -90,6 +90,8 @@ class Engine {
   Device dev_;
   int device_ = 0;
   int batch_ = 0;
+  int f64_gmin_ = 1;
+  bool compact_keys_ = false;  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)
   DevConsts *dC_ = nullptr;
   W2 *dTw_ = nullptr;
   u32 *dIndex_ = nullptr;

@@ -12,9 +12,16 @@ struct TwRef {
   u64 N;
   HD const W2 *fwd(int tab) const { return base + (static_cast<size_t>(tab) * 2) * N; }
   HD const W2 *inv(int tab) const { return base + (static_cast<size_t>(tab) * 2 + 1) * N; }
-  // FP64 tables hold D2 {w, w/q} in the same 16-byte slots
-  HD const D2 *fwd_f(int tab) const { return reinterpret_cast<const D2 *>(fwd(tab)); }
-  HD const D2 *inv_f(int tab) const { return reinterpret_cast<const D2 *>(inv(tab)); }
+  // FP64 tables reuse the same 16 bytes per entry as two planes of N doubles: index-major, then component-major
+  int gmin;
+  HD F64Tw fwd_f(int tab) const {
+    const double *p = reinterpret_cast<const double *>(fwd(tab));
+    return F64Tw{p, p + N, gmin};
+  }
+  HD F64Tw inv_f(int tab) const {
+    const double *p = reinterpret_cast<const double *>(inv(tab));
+    return F64Tw{p, p + N, gmin};
+  }
 };
 
 struct TabMap {  // limb index inside an item -> NTT table id
@@ -49,12 +56,12 @@ struct NttBody {
       }
       SYNC();
       if (!inverse) {
-        ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(tab), qd, qi, 1, nt, 1.0f);
+        ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(tab), qd, qi, 0, 0, nt, 1.0f);
         FOR_THREADS(tid, nt) {
           for (int i = tid; i < S; i += nt) dst[i] = f_canonical(fm[pidx(i)], qd, qi);
         }
       } else {
-        ntt_inv_core_f64<LOGS>(fm, tw.inv_f(tab), qd, qi, 1, nt);
+        ntt_inv_core_f64<LOGS>(fm, tw.inv_f(tab), qd, qi, 0, 0, nt);
         const D2 ninv = C->n_inv_f[tab];
         FOR_THREADS(tid, nt) {
           for (int i = tid; i < S; i += nt) dst[i] = f_canonical(f_mulmod_const(fm[pidx(i)], ninv, qd), qd, qi);
@@ -108,8 +115,8 @@ struct KsDigitsBody {
     double *acc0 = fm + ntt_smem_words(S);
     double *acc1 = acc0 + S;
     const double q = C->qf[k], qi = C->qinvf[k];
-    const D2 *twk = tw.fwd_f(k);
-    const D2 w1 = twk[1];
+    const F64Tw twk = tw.fwd_f(k);
+    const D2 w1{twk.idx[1], f_mul(twk.idx[1], qi)};
     FOR_THREADS(tid, nt) {
       for (int i = tid; i < S; i += nt) acc0[i] = acc1[i] = 0.0;
     }
@@ -136,21 +143,24 @@ struct KsDigitsBody {
                 y = f_reduce(y, q, qi);
               }
               const double t = f_mulmod_const(y, w1, q);
-              fm[pidx(i)] = h ? f_add(x, -t) : f_add(x, t);  // |.| <= 2q
+              fm[pidx(i)] = h ? f_add(x, -t) : f_add(x, t);  // |.| <= 2.5q
             }
           }
         }
       }
       SYNC();
-      ntt_fwd_core_f64<LOGH>(fm, twk, q, qi, 2 + h, nt, 2.0f);
-      const D2 *k0 = reinterpret_cast<const D2 *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
-      const D2 *k1 = k0 + static_cast<size_t>(K) * N;
+      ntt_fwd_core_f64<LOGH>(fm, twk, q, qi, 1, h, nt, 2.5f);
+      // compact FP64 key: double[L][2][K][N] (8 bytes per residue; k/q is formed as k * (1/q))
+      const double *k0 = reinterpret_cast<const double *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+      const double *k1 = k0 + static_cast<size_t>(K) * N;
       FOR_THREADS(tid, nt) {
 #pragma unroll 4
         for (int i = tid; i < S; i += nt) {
           const double v = fm[pidx(i)];
-          acc0[i] = f_add(acc0[i], f_mulmod_const(v, k0[i], q));  // L <= 8 terms of magnitude <= q: exact
-          acc1[i] = f_add(acc1[i], f_mulmod_const(v, k1[i], q));
+          const double a = k0[i], c = k1[i];
+          // L <= 8 terms of magnitude <= 1.5q: |acc| <= 12q < 2^53, every partial sum is an exact integer
+          acc0[i] = f_add(acc0[i], f_mulmod_const(v, D2{a, f_mul(a, qi)}, q));
+          acc1[i] = f_add(acc1[i], f_mulmod_const(v, D2{c, f_mul(c, qi)}, q));
         }
       }
       SYNC();
@@ -512,7 +522,7 @@ struct LiftNttBody {
         }
       }
       SYNC();
-      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 1, nt, 1.0f);
+      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 0, 0, nt, 1.0f);
       u64 *dstf = out + static_cast<size_t>(bid) * S;
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) dstf[j] = f_canonical(fm[pidx(j)], qd, qi);
@@ -566,7 +576,7 @@ struct NttMacBody {
         for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
       }
       SYNC();
-      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 1, nt, 1.0f);
+      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 0, 0, nt, 1.0f);
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) {
           u64 v = f_canonical(f_mulmod_var(fm[pidx(j)], u_to_f(d[j]), qd, qi), qd, qi);
@@ -705,9 +715,10 @@ struct BehzScaleRoundBody {
 struct ShoupifyBody {
   static constexpr const char *kName = "shoupify";
   const u64 *in;  // [L][2][K][N]
-  W2 *out;
+  W2 *out;        // integer limbs: W2 per residue; compact FP64 mode (every key limb on the FP64 path): double per residue
   const DevConsts *C;
   size_t total;
+  int compact_f64;
   HD void operator()(int bid, int nt, unsigned char *) const {
     const size_t N = C->N;
     FOR_THREADS(tid, nt) {
@@ -716,10 +727,8 @@ struct ShoupifyBody {
         const int limb = static_cast<int>((g / N) % C->K);
         const DevMod m = C->mod[limb];
         const u64 w = in[g];
-        if (C->f64[limb]) {  // FP64 limbs keep the key as (k, k/q) doubles in the same 16-byte slot
-          const double wd = u_to_f(w);
-          const D2 dv{wd, wd / C->qf[limb]};
-          reinterpret_cast<D2 *>(out)[g] = dv;
+        if (compact_f64) {
+          reinterpret_cast<double *>(out)[g] = u_to_f(w);
         } else {
         // floor(w * 2^64 / q): Barrett estimate from floor(2^128/q), then exact correction
         u64 est = mulhi64(w, m.cr0) + w * m.cr1;

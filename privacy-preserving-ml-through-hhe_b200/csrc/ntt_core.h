@@ -164,20 +164,47 @@ HD void ntt_inv_core(u64 *sm, const W2 *__restrict__ tw, u64 q, u32 mc, int nt) 
 
 // ---------------------------------------------------------------------------------------------------------------
 // FP64-pipe variants (q <= 2^49, see modarith_f64.h). Shared memory holds doubles (signed integers, |x| < 8q).
-// Bound bookkeeping is in units of q: a forward stage adds at most 1 (|w*b mod q| <= q), an inverse stage doubles.
+//
+// Twiddles are plain doubles w (8 bytes); w/q is formed on the fly as w * (1/q) (one DMUL), which keeps the quotient
+// estimate within 1.5 of the true quotient, so |w*b mod q| <= 1.5 q: bounds below are in units of q, a forward stage
+// adds at most 1.5, an inverse stage doubles.
+//
+// Two table layouts per (modulus, direction), both of N doubles (F64Tw):
+//   idx[k]          index-major, SEAL's order (psi^bitrev(k)): used by passes whose twiddles are warp-uniform
+//   cm[off(g0) + c*2^g0 + H]  component-major for a 3-stage register pass starting at global stage g0: component
+//                   c = 2^d - 1 + j is twiddle j of stage g0+d, H = index of the radix-8 group's 2^(logN-g0) block.
+//                   Consecutive lanes read consecutive doubles (2 L1 wavefronts per component instead of up to 16).
+struct F64Tw {
+  const double *idx;
+  const double *cm;
+  int gmin;  // first global stage that has a component-major table (= logN mod 3, or 3 if that is 0)
+};
+HD size_t f64tw_offset(int g0, int gmin) {
+  size_t off = 0;
+  for (int g = gmin; g < g0; g += 3) off += static_cast<size_t>(7) << g;
+  return off;
+}
 
-template <int R>
-HD void fwd_group_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, int logS, int s0, u32 mc, int g, bool reduce) {
+// Register pass over local stages [s0, s0+R) of the chunk `chunk` of a transform split into 2^lm chunks.
+template <int R, bool INVERSE>
+HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int logS, int s0, int lm, int chunk, int g, bool reduce) {
   constexpr int E = 1 << R;
   const int lg = logS - s0 - R;
   const int lo = g & ((1 << lg) - 1), hi = g >> lg;
   const int base = (hi << (logS - s0)) + lo;
-  D2 wv[E];
+  const int g0 = s0 + lm;                      // global stage of the pass
+  const int H = (chunk << s0) + hi;            // global block index at stage g0
+  double wv[E];
+  if (R == 3 && g0 >= tw.gmin) {
+    const double *T = tw.cm + f64tw_offset(g0, tw.gmin) + H;
 #pragma unroll
-  for (int d = 0; d < R; ++d) {
-    const u32 tb = (mc << (s0 + d)) + (static_cast<u32>(hi) << d);
+    for (int c = 0; c < E - 1; ++c) wv[c + 1] = T[static_cast<size_t>(c) << g0];
+  } else {
 #pragma unroll
-    for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw[tb + j];
+    for (int d = 0; d < R; ++d) {
+#pragma unroll
+      for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw.idx[(static_cast<size_t>(1) << (g0 + d)) + (static_cast<size_t>(H) << d) + j];
+    }
   }
   double x[E];
 #pragma unroll
@@ -186,53 +213,36 @@ HD void fwd_group_f64(double *sm, const D2 *__restrict__ tw, double q, double qi
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = f_reduce(x[e], q, qinv);
   }
+  if (!INVERSE) {
 #pragma unroll
-  for (int d = 0; d < R; ++d) {
-    const int half = E >> (d + 1);
+    for (int d = 0; d < R; ++d) {
+      const int half = E >> (d + 1);
 #pragma unroll
-    for (int j = 0; j < (1 << d); ++j) {
-      const D2 w = wv[(1 << d) + j];
+      for (int j = 0; j < (1 << d); ++j) {
+        const D2 w{wv[(1 << d) + j], f_mul(wv[(1 << d) + j], qinv)};
 #pragma unroll
-      for (int k = 0; k < half; ++k) {
-        double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
-        const double t = f_mulmod_const(b, w, q);
-        b = f_add(a, -t);
-        a = f_add(a, t);
+        for (int k = 0; k < half; ++k) {
+          double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
+          const double t = f_mulmod_const(b, w, q);
+          b = f_add(a, -t);
+          a = f_add(a, t);
+        }
       }
     }
-  }
+  } else {
 #pragma unroll
-  for (int e = 0; e < E; ++e) sm[pidx(base + (e << lg))] = x[e];
-}
-
-template <int R>
-HD void inv_group_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, int logS, int s0, u32 mc, int g) {
-  constexpr int E = 1 << R;
-  const int lg = logS - s0 - R;
-  const int lo = g & ((1 << lg) - 1), hi = g >> lg;
-  const int base = (hi << (logS - s0)) + lo;
-  D2 wv[E];
+    for (int d = R - 1; d >= 0; --d) {
+      const int half = E >> (d + 1);
 #pragma unroll
-  for (int d = 0; d < R; ++d) {
-    const u32 tb = (mc << (s0 + d)) + (static_cast<u32>(hi) << d);
+      for (int j = 0; j < (1 << d); ++j) {
+        const D2 w{wv[(1 << d) + j], f_mul(wv[(1 << d) + j], qinv)};
 #pragma unroll
-    for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw[tb + j];
-  }
-  double x[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) x[e] = f_reduce(sm[pidx(base + (e << lg))], q, qinv);  // |x| <= q/2: R <= 3 doublings stay < 8q
-#pragma unroll
-  for (int d = R - 1; d >= 0; --d) {
-    const int half = E >> (d + 1);
-#pragma unroll
-    for (int j = 0; j < (1 << d); ++j) {
-      const D2 w = wv[(1 << d) + j];
-#pragma unroll
-      for (int k = 0; k < half; ++k) {
-        double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
-        const double dlt = f_add(a, -b);
-        a = f_add(a, b);
-        b = f_mulmod_const(dlt, w, q);
+        for (int k = 0; k < half; ++k) {
+          double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
+          const double dlt = f_add(a, -b);
+          a = f_add(a, b);
+          b = f_mulmod_const(dlt, w, q);
+        }
       }
     }
   }
@@ -242,40 +252,40 @@ HD void inv_group_f64(double *sm, const D2 *__restrict__ tw, double q, double qi
 
 // Forward transform on doubles. bound_in: |input| <= bound_in * q (1 for canonical residues). Output: |x| <= 7.5 q.
 template <int LOGS>
-HD void ntt_fwd_core_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, u32 mc, int nt, float bound_in) {
+HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int lm, int chunk, int nt, float bound_in) {
   constexpr int R0 = NttSchedule<LOGS>::kFirst;
-  static_assert(kRadixLog <= 3, "FP64 bound schedule assumes at most 3 stages per register pass");
+  static_assert(kRadixLog == 3, "FP64 path is written for radix-8 register passes");
   float bound = bound_in;
   {
-    const bool red = bound + R0 > 7.5f;
+    const bool red = bound + 1.5f * R0 > 7.5f;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R0)); g += nt) fwd_group_f64<R0>(sm, tw, q, qinv, LOGS, 0, mc, g, red);
+      for (int g = tid; g < (1 << (LOGS - R0)); g += nt) group_f64<R0, false>(sm, tw, q, qinv, LOGS, 0, lm, chunk, g, red);
     }
     SYNC();
-    bound = (red ? 0.5f : bound) + R0;
+    bound = (red ? 0.5f : bound) + 1.5f * R0;
   }
   for (int s0 = R0; s0 < LOGS; s0 += kRadixLog) {
-    const bool red = bound + kRadixLog > 7.5f;
+    const bool red = bound + 1.5f * kRadixLog > 7.5f;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) fwd_group_f64<kRadixLog>(sm, tw, q, qinv, LOGS, s0, mc, g, red);
+      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) group_f64<kRadixLog, false>(sm, tw, q, qinv, LOGS, s0, lm, chunk, g, red);
     }
     SYNC();
-    bound = (red ? 0.5f : bound) + kRadixLog;
+    bound = (red ? 0.5f : bound) + 1.5f * kRadixLog;
   }
 }
 
-// Inverse transform on doubles (without 1/N). Any |input| < 8q. Output: |x| <= 4q.
+// Inverse transform on doubles (without 1/N). Any |input| < 8q (every pass reduces on load: 3 doublings of q/2 = 4q).
 template <int LOGS>
-HD void ntt_inv_core_f64(double *sm, const D2 *__restrict__ tw, double q, double qinv, u32 mc, int nt) {
+HD void ntt_inv_core_f64(double *sm, F64Tw tw, double q, double qinv, int lm, int chunk, int nt) {
   constexpr int R0 = NttSchedule<LOGS>::kFirst;
   for (int s0 = LOGS - kRadixLog; s0 >= R0; s0 -= kRadixLog) {
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) inv_group_f64<kRadixLog>(sm, tw, q, qinv, LOGS, s0, mc, g);
+      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) group_f64<kRadixLog, true>(sm, tw, q, qinv, LOGS, s0, lm, chunk, g, true);
     }
     SYNC();
   }
   FOR_THREADS(tid, nt) {
-    for (int g = tid; g < (1 << (LOGS - R0)); g += nt) inv_group_f64<R0>(sm, tw, q, qinv, LOGS, 0, mc, g);
+    for (int g = tid; g < (1 << (LOGS - R0)); g += nt) group_f64<R0, true>(sm, tw, q, qinv, LOGS, 0, lm, chunk, g, true);
   }
   SYNC();
 }
