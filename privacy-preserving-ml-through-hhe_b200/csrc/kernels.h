@@ -56,12 +56,12 @@ struct NttBody {
       }
       SYNC();
       if (!inverse) {
-        ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(tab), qd, qi, 0, 0, nt, 1.0f);
+        ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(tab), qd, qi, 0, nt);
         FOR_THREADS(tid, nt) {
           for (int i = tid; i < S; i += nt) dst[i] = f_canonical(fm[pidx(i)], qd, qi);
         }
       } else {
-        ntt_inv_core_f64<LOGS>(fm, tw.inv_f(tab), qd, qi, 0, 0, nt);
+        ntt_inv_core_f64<LOGS, 0>(fm, tw.inv_f(tab), qd, qi, 0, nt);
         const D2 ninv = C->n_inv_f[tab];
         FOR_THREADS(tid, nt) {
           for (int i = tid; i < S; i += nt) dst[i] = f_canonical(f_mulmod_const(fm[pidx(i)], ninv, qd), qd, qi);
@@ -149,7 +149,7 @@ struct KsDigitsBody {
         }
       }
       SYNC();
-      ntt_fwd_core_f64<LOGH>(fm, twk, q, qi, 1, h, nt, 2.5f);
+      ntt_fwd_core_f64<LOGH, 1, 5>(fm, twk, q, qi, h, nt);
       // compact FP64 key: double[L][2][K][N] (8 bytes per residue; k/q is formed as k * (1/q))
       const double *k0 = reinterpret_cast<const double *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
       const double *k1 = k0 + static_cast<size_t>(K) * N;
@@ -522,7 +522,7 @@ struct LiftNttBody {
         }
       }
       SYNC();
-      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 0, 0, nt, 1.0f);
+      ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
       u64 *dstf = out + static_cast<size_t>(bid) * S;
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) dstf[j] = f_canonical(fm[pidx(j)], qd, qi);
@@ -576,7 +576,7 @@ struct NttMacBody {
         for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
       }
       SYNC();
-      ntt_fwd_core_f64<LOGS>(fm, tw.fwd_f(i), qd, qi, 0, 0, nt, 1.0f);
+      ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) {
           u64 v = f_canonical(f_mulmod_var(fm[pidx(j)], u_to_f(d[j]), qd, qi), qd, qi);

@@ -185,30 +185,33 @@ HD size_t f64tw_offset(int g0, int gmin) {
   return off;
 }
 
-// Register pass over local stages [s0, s0+R) of the chunk `chunk` of a transform split into 2^lm chunks.
-template <int R, bool INVERSE>
-HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int logS, int s0, int lm, int chunk, int g, bool reduce) {
+// Register pass over local stages [S0, S0+R) of chunk `chunk` of a transform that was split into 2^LM chunks.
+// Every stride is a compile-time constant, so shared-memory and twiddle accesses use immediate offsets.
+template <int R, bool INVERSE, int LOGS, int S0, int LM>
+HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, bool reduce) {
   constexpr int E = 1 << R;
-  const int lg = logS - s0 - R;
-  const int lo = g & ((1 << lg) - 1), hi = g >> lg;
-  const int base = (hi << (logS - s0)) + lo;
-  const int g0 = s0 + lm;                      // global stage of the pass
-  const int H = (chunk << s0) + hi;            // global block index at stage g0
+  constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
+  constexpr int G0 = S0 + LM;        // global stage of the pass
+  const int lo = g & ((1 << LG) - 1), hi = g >> LG;
+  const int H = (chunk << S0) + hi;  // global block index at stage G0
+  // padded shared-memory offsets: pidx(base + (e << LG)) = a0 + off(e) with compile-time off(e)
+  const int a0 = pidx(hi << (LOGS - S0)) + lo + (LG >= 4 ? (lo >> 4) : 0);
+  auto off = [](int e) constexpr { return LG >= 4 ? e * ((1 << LG) + (1 << (LG >= 4 ? LG - 4 : 0))) : (e << LG) + (e >> (LG < 4 ? 4 - LG : 0)); };
   double wv[E];
-  if (R == 3 && g0 >= tw.gmin) {
-    const double *T = tw.cm + f64tw_offset(g0, tw.gmin) + H;
+  if (R == 3 && G0 >= 1 && (G0 % 3) == ((LOGS + LM) % 3)) {
+    const double *T = tw.cm + f64tw_offset(G0, tw.gmin) + H;
 #pragma unroll
-    for (int c = 0; c < E - 1; ++c) wv[c + 1] = T[static_cast<size_t>(c) << g0];
+    for (int c = 0; c < E - 1; ++c) wv[c + 1] = T[static_cast<size_t>(c) << G0];
   } else {
 #pragma unroll
     for (int d = 0; d < R; ++d) {
 #pragma unroll
-      for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw.idx[(static_cast<size_t>(1) << (g0 + d)) + (static_cast<size_t>(H) << d) + j];
+      for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw.idx[(static_cast<size_t>(1) << (G0 + d)) + (static_cast<size_t>(H) << d) + j];
     }
   }
   double x[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) x[e] = sm[pidx(base + (e << lg))];
+  for (int e = 0; e < E; ++e) x[e] = sm[a0 + off(e)];
   if (reduce) {
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = f_reduce(x[e], q, qinv);
@@ -216,6 +219,8 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int logS, int s0,
   if (!INVERSE) {
 #pragma unroll
     for (int d = 0; d < R; ++d) {
+      constexpr int dummy = 0;
+      (void)dummy;
       const int half = E >> (d + 1);
 #pragma unroll
       for (int j = 0; j < (1 << d); ++j) {
@@ -247,47 +252,51 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int logS, int s0,
     }
   }
 #pragma unroll
-  for (int e = 0; e < E; ++e) sm[pidx(base + (e << lg))] = x[e];
+  for (int e = 0; e < E; ++e) sm[a0 + off(e)] = x[e];
 }
 
-// Forward transform on doubles. bound_in: |input| <= bound_in * q (1 for canonical residues). Output: |x| <= 7.5 q.
-template <int LOGS>
-HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int lm, int chunk, int nt, float bound_in) {
-  constexpr int R0 = NttSchedule<LOGS>::kFirst;
+// Compile-time chain of forward passes. B2 = twice the bound (in units of q) of the values entering the pass; a pass
+// of R stages adds 1.5 R; values must stay below 8q at every stage input, i.e. the bound after the pass <= 7.5 q.
+template <int LOGS, int LM, int S0, int B2>
+struct FwdChainF64 {
+  static constexpr int R = S0 == 0 ? NttSchedule<LOGS>::kFirst : kRadixLog;
+  static constexpr bool kReduce = B2 + 3 * R > 15;
+  static constexpr int kOut = (kReduce ? 1 : B2) + 3 * R;
+  static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+    FOR_THREADS(tid, nt) {
+      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, false, LOGS, S0, LM>(sm, tw, q, qinv, chunk, g, kReduce);
+    }
+    SYNC();
+    if (S0 + R < LOGS) FwdChainF64<LOGS, LM, (S0 + R < LOGS ? S0 + R : 0), (S0 + R < LOGS ? kOut : 0)>::run_next(sm, tw, q, qinv, chunk, nt);
+  }
+  static HD void run_next(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) { run(sm, tw, q, qinv, chunk, nt); }
+};
+
+// Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues). Output < 8q.
+template <int LOGS, int LM, int B2IN>
+HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
   static_assert(kRadixLog == 3, "FP64 path is written for radix-8 register passes");
-  float bound = bound_in;
-  {
-    const bool red = bound + 1.5f * R0 > 7.5f;
-    FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R0)); g += nt) group_f64<R0, false>(sm, tw, q, qinv, LOGS, 0, lm, chunk, g, red);
-    }
-    SYNC();
-    bound = (red ? 0.5f : bound) + 1.5f * R0;
-  }
-  for (int s0 = R0; s0 < LOGS; s0 += kRadixLog) {
-    const bool red = bound + 1.5f * kRadixLog > 7.5f;
-    FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) group_f64<kRadixLog, false>(sm, tw, q, qinv, LOGS, s0, lm, chunk, g, red);
-    }
-    SYNC();
-    bound = (red ? 0.5f : bound) + 1.5f * kRadixLog;
-  }
+  FwdChainF64<LOGS, LM, 0, B2IN>::run(sm, tw, q, qinv, chunk, nt);
 }
 
-// Inverse transform on doubles (without 1/N). Any |input| < 8q (every pass reduces on load: 3 doublings of q/2 = 4q).
-template <int LOGS>
-HD void ntt_inv_core_f64(double *sm, F64Tw tw, double q, double qinv, int lm, int chunk, int nt) {
-  constexpr int R0 = NttSchedule<LOGS>::kFirst;
-  for (int s0 = LOGS - kRadixLog; s0 >= R0; s0 -= kRadixLog) {
+// Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2 = 4q < 8q).
+template <int LOGS, int LM, int S0>
+struct InvChainF64 {
+  static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+    constexpr int R0 = NttSchedule<LOGS>::kFirst;
+    constexpr int R = S0 == 0 ? R0 : kRadixLog;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - kRadixLog)); g += nt) group_f64<kRadixLog, true>(sm, tw, q, qinv, LOGS, s0, lm, chunk, g, true);
+      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, true, LOGS, S0, LM>(sm, tw, q, qinv, chunk, g, true);
     }
     SYNC();
+    if (S0 > 0) InvChainF64<LOGS, LM, (S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt);
   }
-  FOR_THREADS(tid, nt) {
-    for (int g = tid; g < (1 << (LOGS - R0)); g += nt) group_f64<R0, true>(sm, tw, q, qinv, LOGS, 0, lm, chunk, g, true);
-  }
-  SYNC();
+};
+
+template <int LOGS, int LM>
+HD void ntt_inv_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+  constexpr int R0 = NttSchedule<LOGS>::kFirst;
+  InvChainF64<LOGS, LM, (LOGS - kRadixLog >= R0 ? LOGS - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt);
 }
 
 }  // namespace hhe
