@@ -284,6 +284,9 @@ def main():
         same = np.array_equal(out_host[0].numpy().view(np.uint64), d_out[0].cpu().numpy().view(np.uint64))
         assert same, "host-API and device-API outputs differ"
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
@@ -302,7 +305,7 @@ def main():
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": KS_BYTES * B, "avg_launch_ms": avg_ms, "launches": ks["launches"],
         "share_of_kernel_time": ks["ms"] / kernel_ms if kernel_ms else None, "dominant_by_time": dom[0],
-        "note": "64-bit modular-integer kernel: bounded by the INT32/IMAD pipe, not HBM (see DESIGN.md, profiles/)",
+        "note": "exact 64-bit modular arithmetic: bounded by instruction issue / the FP64 and IMAD pipes, not HBM (see DESIGN.md, profiles/)",
         "step_level": {"algorithmic_bytes_per_block": BYTES_PER_BLOCK[bool(args.bsgs)],
                        "achieved": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9,
                        "frac": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9 / peak},

@@ -120,36 +120,69 @@ struct KsDigitsBody {
     FOR_THREADS(tid, nt) {
       for (int i = tid; i < S; i += nt) acc0[i] = acc1[i] = 0.0;
     }
+    // When the sub-transform's odd-sized first pass is a single stage it is folded into the load as well: the thread
+    // that owns residues i and i + S/2 applies global stages 0 and 1 before anything is written to shared memory.
+    constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
+    const D2 w2{twk.idx[2 + h], f_mul(twk.idx[2 + h], qi)};
     for (int J = 0; J < L; ++J) {
       const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
-      const bool reduce = C->mod[J].q > C->mod[k].q;
-      FOR_THREADS(tid, nt) {
-        constexpr int U = 4;
-        for (int i0 = tid; i0 < S; i0 += nt * U) {
-          u64 xs[U], ys[U];
+      // digits are residues mod q_J < 2 q_k (all primes of a parameter set have the same size): as doubles they are
+      // valid inputs (< 8 q_k) without re-reduction
+      if (kFold) {
+        FOR_THREADS(tid, nt) {
+          constexpr int U = 2;
+          for (int i0 = tid; i0 < S / 2; i0 += nt * U) {
+            u64 v[U][4];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * nt;
-            xs[u] = i < S ? dig[i] : 0;
-            ys[u] = i < S ? dig[i + S] : 0;
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * nt;
-            if (i < S) {
-              double x = u_to_f(xs[u]), y = u_to_f(ys[u]);  // digits are < q_J < 2^52
-              if (reduce) {
-                x = f_reduce(x, q, qi);
-                y = f_reduce(y, q, qi);
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * nt;
+              if (i < S / 2) {
+                v[u][0] = dig[i];
+                v[u][1] = dig[i + S];
+                v[u][2] = dig[i + S / 2];
+                v[u][3] = dig[i + S / 2 + S];
               }
-              const double t = f_mulmod_const(y, w1, q);
-              fm[pidx(i)] = h ? f_add(x, -t) : f_add(x, t);  // |.| <= 2.5q
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * nt;
+              if (i < S / 2) {
+                const double t0 = f_mulmod_const(u_to_f(v[u][1]), w1, q), t1 = f_mulmod_const(u_to_f(v[u][3]), w1, q);
+                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);  // |.| <= 3.5q
+                const double a1 = h ? f_add(u_to_f(v[u][2]), -t1) : f_add(u_to_f(v[u][2]), t1);
+                const double tt = f_mulmod_const(a1, w2, q);
+                fm[pidx(i)] = f_add(a0, tt);  // |.| <= 5q
+                fm[pidx(i + S / 2)] = f_add(a0, -tt);
+              }
             }
           }
         }
+        SYNC();
+        ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), 10>(fm, twk, q, qi, h, nt);
+      } else {
+        FOR_THREADS(tid, nt) {
+          constexpr int U = 4;
+          for (int i0 = tid; i0 < S; i0 += nt * U) {
+            u64 xs[U], ys[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * nt;
+              xs[u] = i < S ? dig[i] : 0;
+              ys[u] = i < S ? dig[i + S] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * nt;
+              if (i < S) {
+                const double t = f_mulmod_const(u_to_f(ys[u]), w1, q);
+                fm[pidx(i)] = h ? f_add(u_to_f(xs[u]), -t) : f_add(u_to_f(xs[u]), t);  // |.| <= 3.5q
+              }
+            }
+          }
+        }
+        SYNC();
+        ntt_fwd_core_f64<LOGH, 1, 7>(fm, twk, q, qi, h, nt);
       }
-      SYNC();
-      ntt_fwd_core_f64<LOGH, 1, 5>(fm, twk, q, qi, h, nt);
       // compact FP64 key: double[L][2][K][N] (8 bytes per residue; k/q is formed as k * (1/q))
       const double *k0 = reinterpret_cast<const double *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
       const double *k1 = k0 + static_cast<size_t>(K) * N;
@@ -283,7 +316,7 @@ struct ModDownBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const size_t b = g / N, j = g % N;
+        const size_t b = g >> C->logn, j = g & (N - 1);
         const DevMod msp = C->mod[K - 1];
         for (int c = 0; c < 2; ++c) {
           const u64 *a = acc + ((b * 2 + c) * K) * N + j;
@@ -320,8 +353,8 @@ struct GaloisBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const size_t limb = g / N, idx = g % N;
-        const u64 q = C->mod[limb % C->L].q;
+        const size_t limb = g >> C->logn, idx = g & (N - 1);
+        const u64 q = C->mod[static_cast<u32>(limb) % static_cast<u32>(C->L)].q;
         const u64 ip = (idx * elt_inv) & (2 * N - 1);
         u64 v = in[limb * N + (ip & (N - 1))];
         if (ip >= N) v = neg_mod(v, q);
@@ -345,7 +378,7 @@ struct AddBody {  // out = a + b
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const u64 q = C->mod[(g / N) % limbs % C->L].q;
+        const u64 q = C->mod[static_cast<u32>(g >> C->logn) % static_cast<u32>(limbs) % static_cast<u32>(C->L)].q;
         out[g] = add_mod(a[g], b[g], q);
       }
     }
@@ -362,7 +395,7 @@ struct NegateBody {
     const size_t N = C->N;
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
-      if (g < total) out[g] = neg_mod(a[g], C->mod[(g / N) % C->L].q);
+      if (g < total) out[g] = neg_mod(a[g], C->mod[static_cast<u32>(g >> C->logn) % static_cast<u32>(C->L)].q);
     }
   }
 };
@@ -384,10 +417,11 @@ struct AddPlainBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const size_t limb = g / N, j = g % N;
-        const int i = static_cast<int>(limb % L);
-        const size_t item = limb / (2 * L);
-        const int comp = static_cast<int>((limb / L) & 1);
+        const u32 limb = static_cast<u32>(g >> C->logn);
+        const size_t j = g & (N - 1);
+        const int i = static_cast<int>(limb % static_cast<u32>(L));
+        const size_t item = limb / static_cast<u32>(2 * L);
+        const int comp = static_cast<int>((limb / static_cast<u32>(L)) & 1);
         const DevMod mi = C->mod[i];
         u64 v = a[g];
         if (negate) v = neg_mod(v, mi.q);
@@ -617,7 +651,7 @@ struct BehzExtendBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const size_t p = g / N, j = g % N;
+        const size_t p = g >> C->logn, j = g & (N - 1);
         u64 z[kMaxLimbs];
         u32 mt = 0;
         for (int i = 0; i < L; ++i) {
@@ -652,7 +686,9 @@ struct TensorBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const size_t j = g % N, l = (g / N) % limbs, item = g / (N * limbs);
+        const size_t j = g & (N - 1);
+        const u32 lidx = static_cast<u32>(g >> C->logn);
+        const size_t l = lidx % static_cast<u32>(limbs), item = lidx / static_cast<u32>(limbs);
         const DevMod m = C->mod[tab0 + l];
         const size_t poly = static_cast<size_t>(limbs) * N, off = l * N + j;
         const u64 a0 = a[item * 2 * poly + off], a1 = a[item * 2 * poly + poly + off];
@@ -680,7 +716,7 @@ struct BehzScaleRoundBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const size_t p = g / N, j = g % N;
+        const size_t p = g >> C->logn, j = g & (N - 1);
         u64 z[kMaxLimbs], f[kMaxLimbs];
         for (int i = 0; i < L; ++i) z[i] = mul_shoup(dq[(p * L + i) * N + j], C->t_ipq[i], C->mod[i].q);
         for (int bb = 0; bb <= L; ++bb) {
@@ -724,7 +760,7 @@ struct ShoupifyBody {
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
-        const int limb = static_cast<int>((g / N) % C->K);
+        const int limb = static_cast<int>(static_cast<u32>(g >> C->logn) % static_cast<u32>(C->K));
         const DevMod m = C->mod[limb];
         const u64 w = in[g];
         if (compact_f64) {

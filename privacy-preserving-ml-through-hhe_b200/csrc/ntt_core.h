@@ -279,6 +279,12 @@ HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk,
   FwdChainF64<LOGS, LM, 0, B2IN>::run(sm, tw, q, qinv, chunk, nt);
 }
 
+// Same, entering the chain at local stage S0 (the caller already performed the stages below S0).
+template <int LOGS, int LM, int S0, int B2IN>
+HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+  FwdChainF64<LOGS, LM, S0, B2IN>::run(sm, tw, q, qinv, chunk, nt);
+}
+
 // Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2 = 4q < 8q).
 template <int LOGS, int LM, int S0>
 struct InvChainF64 {

@@ -275,3 +275,32 @@ def test_golden_material(eng512):
 def test_golden_transciphering(eng512):
     got = eng512.pasta3_decompose(FX["enc_key"], FX["sym_ct"])
     assert np.array_equal(got, FX["decomposed"])
+
+
+# ---- N=2048: log2(N/2) = 10 = 1 mod 3, the same pass schedule class as N=16384 (13 = 1 mod 3): covers the key-switch
+# prologue that folds two Cooley-Tukey stages into the load, which the N=1024 / N=512 rings do not reach -------------
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_n2048_fold_schedule(backend):
+    NN = 2048
+    q = common.small_params(NN, 3, 48)
+    orc = O.Oracle(NN, common.T, q)
+    keys = ToyKeys(orc, 5)
+    ctx = make_ctx(backend, NN, q)
+    assert ctx.info()["fp64_moduli"] == len(q)
+    e1 = orc.galois_elt(-1)
+    for kind, elt, k in ((0, e1, keys.galois_key(e1)), (2, 0, keys.relin_key())):
+        orc.load_ksk(kind, elt, k)
+        ctx.load_ksk(kind, elt, k)
+    rng = np.random.default_rng(3)
+    a = keys.encrypt_zero_plus(orc, orc.encode(rng.integers(0, common.T, NN, dtype=np.uint64)))
+    b = keys.encrypt_zero_plus(orc, orc.encode(rng.integers(0, common.T, NN, dtype=np.uint64)))
+    assert np.array_equal(ctx.rotate_rows(a, -1), orc.rotate_rows(a, -1))
+    m3 = orc.multiply(a, b)
+    assert np.array_equal(ctx.multiply(a, b), m3)
+    assert np.array_equal(ctx.relinearize(m3), orc.relinearize(m3))
+    pt = orc.encode(rng.integers(0, common.T, 500, dtype=np.uint64))
+    assert np.array_equal(ctx.multiply_plain(a, pt), orc.multiply_plain(a, pt))
+    x = rng.integers(0, int(q[1]), NN, dtype=np.uint64)
+    assert np.array_equal(ctx.ntt(1, x), orc.ntt(1, x)) and np.array_equal(ctx.ntt(1, x, inverse=True), orc.ntt(1, x, inverse=True))
+    ctx.close()
+    orc.close()
