@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -18,6 +19,11 @@ inline size_t ew_grid(size_t total) { return (total + kEwThreads - 1) / kEwThrea
 inline int ntt_threads(int logS) {
   int groups = 1 << (logS - kRadixLog);
   return std::max(32, std::min(HHE_MAX_THREADS, groups));
+}
+
+bool getenv_flag(const char *name) {
+  const char *v = std::getenv(name);
+  return v && *v && *v != '0';
 }
 
 TabMap map_mod(int limbs, int period, int base) {
@@ -117,6 +123,7 @@ Engine::~Engine() {
   cudaStreamSynchronize(dev_.stream);
 #endif
   for (auto &kv : keys_) dev_.dfree(kv.second);
+  for (auto &kv : perms_) dev_.dfree(kv.second);
   for (auto &c : chunks_) dev_.dfree(c.ptr);
   dev_.dfree(dC_);
   dev_.dfree(dTw_);
@@ -188,9 +195,9 @@ const W2 *Engine::need_key(int kind, u32 elt) const {
 }
 
 // ------------------------------------------------------------------------------------------------ primitives
-void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse) {
+void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride) {
   HHE_DISPATCH_LOG(P_.logn, {
-    NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0};
+    NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, item_stride ? item_stride : static_cast<size_t>(limbs) << LOGV};
     dev_.launch(body, items * limbs, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
 }
@@ -240,11 +247,40 @@ void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
   });
 }
 
-void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first) {
+void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps, size_t sum_off,
+                     u64 *ntt_out) {
   HHE_DISPATCH_LOG(P_.logn, {
-    NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0};
-    dev_.launch(body, items * 2 * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out};
+    dev_.launch(body, items * comps * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
+}
+
+void Engine::strided_copy(const u64 *src, size_t sstride, u64 *dst, size_t dstride, size_t words, size_t rows) {
+  StridedCopyBody body{src, dst, sstride, dstride, words, words * rows};
+  dev_.launch(body, ew_grid(words * rows), kEwThreads, 0);
+}
+
+// Permutation of NTT slots induced by X -> X^elt: slot i holds a(psi^(2*bitrev(i)+1)), so galois(a) at slot i is a at
+// the slot whose exponent is (2*bitrev(i)+1)*elt mod 2N  (cf. GaloisTool::apply_galois_ntt, seal/util/galois.h:78).
+const u32 *Engine::ntt_perm(u32 elt) {
+  auto it = perms_.find(elt);
+  if (it != perms_.end()) return it->second;
+  const u64 N = P_.N, m = 2 * N;
+  auto brev = [&](u64 x) {
+    u64 r = 0;
+    for (int i = 0; i < P_.logn; ++i, x >>= 1) r = (r << 1) | (x & 1);
+    return r;
+  };
+  std::vector<u32> table(N);
+  for (u64 i = 0; i < N; ++i) {
+    const u64 e = ((2 * brev(i) + 1) * elt) % m;
+    table[i] = static_cast<u32>(brev((e - 1) >> 1));
+  }
+  u32 *d = static_cast<u32 *>(dev_.dmalloc(N * sizeof(u32)));
+  dev_.h2d(d, table.data(), N * sizeof(u32));
+  dev_.sync();
+  perms_[elt] = d;
+  return d;
 }
 
 void Engine::ct_intt(u64 *ct, size_t items, int size) {
@@ -273,7 +309,7 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
   u64 *acc = scratch(items * 2 * K * P_.N);
   HHE_DISPATCH_LOG(P_.logn - 1, {
     constexpr int S = 1 << LOGV;
-    KsDigitsBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items)};
+    KsDigitsBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items), nullptr, 0, nullptr};
     dev_.launch(body, items * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
   });
   ntt(acc, acc, items, 2 * K, map_mod(2 * K, K, 0), true);
@@ -416,6 +452,63 @@ void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb) {
   ntt(sum, state, nb, 2 * P_.L, map_mod(2 * P_.L, P_.L, 0), true);
 }
 
+// Same computation with the rotating state kept NTT-resident (see kernels.h "NTT-resident rotation chain"): per
+// rotation 64 + 10 + 8 + 8 limb transforms instead of 72 + 18 + 16. Used when every coefficient prime is on the FP64
+// path; bit-identical to affine_diagonal (tests/test_engine_parity.py compares both rings with the oracle).
+void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb) {
+  Scope sc(*this);
+  const int L = P_.L, K = P_.K;
+  const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(L) * N;
+  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nb * N), *D = scratch(nb * dw);
+  u64 *stn = scratch(nb * ctw), *c0a = scratch(nb * dw), *c0b = scratch(nb * dw), *c1c = scratch(nb * dw), *c1n = scratch(nb * dw),
+      *g1 = scratch(nb * dw), *acc = scratch(nb * 2 * K * N);
+  if (N / 2 != kPastaT) {
+    rotate_rows(state, kPastaT, 0, tmp, nb);
+    add(state, tmp, state, nb);
+  }
+  const u32 e1 = P_.galois_elt_from_step(-1);
+  const W2 *k1 = need_key(0, e1);
+  const u32 *perm = ntt_perm(e1);
+  const u32 e1_inv = inv_mod_2n(e1, 2 * N);
+  // step 0: sum = NTT(state) * D_0, keeping NTT(state)
+  encode_material(mat, nullptr, kDiag, layer, 0, pt, nb);
+  lift_ntt(pt, D, nb);
+  ntt_mac(state, D, dw, sum, nb, true, 2, 0, stn);
+  strided_copy(stn, ctw, c0a, dw, dw, nb);
+  strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
+  strided_copy(state + dw, ctw, c1c, dw, dw, nb);
+  TabMap m10{};
+  m10.id[0] = static_cast<unsigned char>(K - 1);
+  for (int k = 0; k < K; ++k) m10.id[1 + k] = static_cast<unsigned char>(k);
+  u64 *c0_in = c0a, *c0_out = c0b;
+  for (int i = 1; i < kPastaT; ++i) {
+    {  // g1 = galois(c1) in coefficient form: the digits of the key switch
+      GaloisBody gb{c1c, g1, dC_, e1_inv, nb * dw};
+      dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
+    }
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      constexpr int S = 1 << LOGV;
+      KsDigitsBody<LOGV> body{g1, dw, k1, acc, dC_, twref(), static_cast<int>(nb), c1n, dw, perm};
+      dev_.launch(body, nb * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
+    });
+    // inverse NTT of acc[0][special] and acc[1][*]: K + 1 limbs that are contiguous inside each item
+    ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, K + 1, m10, true, static_cast<size_t>(2) * K * N);
+    {
+      ModDownC1Body md{acc, c1c, dC_, nb * N};
+      dev_.launch(md, ew_grid(nb * N), kEwThreads, 0);
+    }
+    encode_material(mat, nullptr, kDiag, layer, i, pt, nb);
+    lift_ntt(pt, D, nb);
+    HHE_DISPATCH_LOG(P_.logn, {
+      Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref()};
+      dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    std::swap(c0_in, c0_out);
+    ntt_mac(c1c, D, dw, sum, nb, false, 1, dw, c1n);
+  }
+  ntt(sum, state, nb, 2 * L, map_mod(2 * L, L, 0), true);
+}
+
 // PASTA_SEAL::babystep_giantstep (src/pasta/pasta_3_seal.cpp:267-366), N1 = 16, N2 = 8
 void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb) {
   constexpr int N1 = 16, N2 = 8;
@@ -472,6 +565,8 @@ void Engine::pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_le
   for (int layer = 0; layer < 4; ++layer) {
     if (use_bsgs)
       affine_bsgs(state, mat, layer, nb);
+    else if (compact_keys_ && !getenv_flag("HHE_NO_RESIDENT"))
+      affine_diagonal_resident(state, mat, layer, nb);
     else
       affine_diagonal(state, mat, layer, nb);
     encode_material(mat, nullptr, kRc, layer, 0, pt, nb);  // add_rc (:205-211)

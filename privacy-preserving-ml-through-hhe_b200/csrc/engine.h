@@ -41,7 +41,7 @@ class Engine {
   const W2 *find_key(int kind, u32 elt) const;
 
   // ---- primitives (device pointers) ----
-  void ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse);
+  void ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride = 0);
   void add(const u64 *a, const u64 *b, u64 *out, size_t items, int size = 2);
   void negate(const u64 *a, u64 *out, size_t items);
   void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first);
@@ -49,7 +49,8 @@ class Engine {
   void encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items);
   void encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items);
   void lift_ntt(const u64 *pt, u64 *D, size_t items);
-  void ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first);
+  void ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps = 2, size_t sum_off = 0,
+               u64 *ntt_out = nullptr);
   void ct_intt(u64 *ct, size_t items, int size = 2);
   void multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items);
   void galois(const u64 *a, u32 elt, u64 *out, size_t items);
@@ -81,6 +82,9 @@ class Engine {
   void pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb, u64 nonce,
                    bool use_bsgs, u64 *d_out);
   void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb);
+  void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb);
+  void strided_copy(const u64 *src, size_t sstride, u64 *dst, size_t dstride, size_t words, size_t rows);
+  const u32 *ntt_perm(u32 elt);
   void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb);
   void feistel(u64 *state, size_t nb);
   const W2 *need_key(int kind, u32 elt) const;
@@ -97,6 +101,7 @@ class Engine {
   u32 *dIndex_ = nullptr;
   u64 *dFeistel_ = nullptr;  // cached NTT of the lifted Feistel mask, [L][N]
   std::map<std::pair<int, u32>, W2 *> keys_;
+  std::map<u32, u32 *> perms_;  // Galois element -> permutation of NTT slots (device)
   struct Chunk {
     u64 *ptr;
     size_t words, used;

@@ -41,13 +41,15 @@ struct NttBody {
   TabMap map;
   int limbs;
   int inverse;
+  size_t istride;  // words between consecutive items (limbs * N when dense)
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     u64 *sm = reinterpret_cast<u64 *>(smem);
     const int tab = map.id[bid % limbs];
     const u64 q = C->mod[tab].q;
-    const u64 *src = in + static_cast<size_t>(bid) * S;
-    u64 *dst = out + static_cast<size_t>(bid) * S;
+    const size_t at = static_cast<size_t>(bid / limbs) * istride + static_cast<size_t>(bid % limbs) * S;
+    const u64 *src = in + at;
+    u64 *dst = out + at;
     if (C->f64[tab]) {  // FP64-pipe transform (modarith_f64.h)
       double *fm = reinterpret_cast<double *>(smem);
       const double qd = C->qf[tab], qi = C->qinvf[tab];
@@ -106,6 +108,12 @@ struct KsDigitsBody {
   const DevConsts *C;
   TwRef tw;
   int count;
+  // Optional (FP64 path): reuse[b][J] = NTT_J(c_J) of the polynomial whose Galois image is the target, and the NTT-domain
+  // permutation of that Galois element. Then NTT_J(target_J) = reuse[b][J][perm[.]] and digit J needs no transform on
+  // key limb k = J (8 of the 72 digit transforms of a key switch).
+  const u64 *reuse;
+  size_t reuse_stride;
+  const u32 *perm;
   // FP64-pipe version of the same computation (q_k <= 2^49): digits, twiddles, key and accumulators are doubles.
   HD void run_f64(int b, int k, int h, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGH;
@@ -128,7 +136,14 @@ struct KsDigitsBody {
       const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
       // digits are residues mod q_J < 2 q_k (all primes of a parameter set have the same size): as doubles they are
       // valid inputs (< 8 q_k) without re-reduction
-      if (kFold) {
+      if (reuse && J == k) {
+        const u64 *rn = reuse + static_cast<size_t>(b) * reuse_stride + static_cast<size_t>(J) * N;
+        const u32 *pm = perm + static_cast<size_t>(h) * S;
+        FOR_THREADS(tid, nt) {
+          for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(rn[pm[i]]);
+        }
+        SYNC();
+      } else if (kFold) {
         FOR_THREADS(tid, nt) {
           constexpr int U = 2;
           for (int i0 = tid; i0 < S / 2; i0 += nt * U) {
@@ -593,16 +608,21 @@ struct NttMacBody {
   const DevConsts *C;
   TwRef tw;
   int first;  // 1: overwrite
+  int comps;  // polynomials per item in `ct` (2: whole ciphertexts, 1: one component)
+  size_t sum_stride, sum_off;  // sum limb (item, c, i) lives at sum + item*sum_stride + sum_off + (c*L + i)*N
+  u64 *ntt_out;                // optional: NTT_i(ct) itself (canonical), same indexing as ct
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     u64 *sm = reinterpret_cast<u64 *>(smem);
     const int L = C->L, i = bid % L;
-    const size_t item = bid / (2 * L);
+    const size_t item = bid / (comps * L);
+    const int cl = bid % (comps * L);
     const DevMod mi = C->mod[i];
     const u64 q = mi.q;
     const u64 *src = ct + static_cast<size_t>(bid) * S;
     const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
-    u64 *dst = sum + static_cast<size_t>(bid) * S;
+    u64 *dst = sum + item * sum_stride + sum_off + static_cast<size_t>(cl) * S;
+    u64 *nout = ntt_out ? ntt_out + static_cast<size_t>(bid) * S : nullptr;
     if (C->f64[i]) {
       double *fm = reinterpret_cast<double *>(smem);
       const double qd = C->qf[i], qi = C->qinvf[i];
@@ -613,6 +633,7 @@ struct NttMacBody {
       ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) {
+          if (nout) nout[j] = f_canonical(fm[pidx(j)], qd, qi);
           u64 v = f_canonical(f_mulmod_var(fm[pidx(j)], u_to_f(d[j]), qd, qi), qd, qi);
           if (!first) v = add_mod(v, dst[j], q);
           dst[j] = v;
@@ -627,6 +648,7 @@ struct NttMacBody {
     ntt_fwd_core<LOGS>(sm, tw.fwd(i), q, 1, nt);
     FOR_THREADS(tid, nt) {
       for (int j = tid; j < S; j += nt) {
+        if (nout) nout[j] = barrett64(sm[pidx(j)], mi);
         u64 v = mul_mod(sm[pidx(j)], d[j], mi);
         if (!first) v = add_mod(v, dst[j], q);
         dst[j] = v;
@@ -742,6 +764,106 @@ struct BehzScaleRoundBody {
           s = upper ? mul_add_mod(msk.q - alpha, C->pb_mod_q[jq], s, mq) : mul_add_mod(alpha, mq.q - C->pb_mod_q[jq], s, mq);
           out[(p * L + jq) * N + j] = s;
         }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Pieces of the NTT-resident rotation chain of the PASTA diagonal loop (Engine::affine_diagonal_resident).
+// Component 0 of the rotating state is kept in the NTT domain for the whole layer:
+//   c0' = galois(c0) + k0,  k0 = (INTT(acc0) - corr) * q_sp^-1,  corr[j] = (r0[j] mod q_i) - (half mod q_i)
+//   =>  NTT(c0') = perm(NTT(c0)) + (acc0 - NTT(corr)) * q_sp^-1          (perm = the automorphism on NTT slots)
+// which needs one inverse NTT (special limb) + L forward NTTs of corr instead of K inverse + L forward NTTs, and the
+// plaintext product for component 0 becomes element-wise. Exact: every step is linear over Z_q_i.
+
+// rows x words strided copy
+struct StridedCopyBody {
+  static constexpr const char *kName = "strided_copy";
+  const u64 *src;
+  u64 *dst;
+  size_t sstride, dstride, words, total;  // total = rows * words
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t r = g / words, w = g % words;
+        dst[r * dstride + w] = src[r * sstride + w];
+      }
+    }
+  }
+};
+
+// ModDown of component 1 only: c1[i][j] = (acc1[i][j] - (r1[j] mod q_i) + half_i) * q_sp^-1, acc1 in coefficient form
+struct ModDownC1Body {
+  static constexpr const char *kName = "moddown_c1";
+  const u64 *acc;  // [count][2][K][N]
+  u64 *out;        // [count][L][N]
+  const DevConsts *C;
+  size_t total;  // count * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const int K = C->K, L = C->L;
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t b = g >> C->logn, j = g & (N - 1);
+        const DevMod msp = C->mod[K - 1];
+        const u64 *a = acc + ((b * 2 + 1) * K) * N + j;
+        const u64 r = csub(a[static_cast<size_t>(K - 1) * N] + C->half_sp, msp.q);
+        for (int i = 0; i < L; ++i) {
+          const DevMod mi = C->mod[i];
+          const u64 ri = msp.q > mi.q ? barrett64(r, mi) : r;
+          u64 v = add_mod(sub_mod(a[static_cast<size_t>(i) * N], ri, mi.q), C->half_sp_mod_q[i], mi.q);
+          out[(b * L + i) * N + j] = mul_shoup(v, C->inv_sp_mod_q[i], mi.q);
+        }
+      }
+    }
+  }
+};
+
+// NTT of the component-0 correction + update of the NTT-resident c0 + plaintext product. CTA per (item, limb i).
+template <int LOGS>
+struct Corr0MacBody {
+  static constexpr const char *kName = "corr0_mac";
+  const u64 *acc;     // [items][2][K][N]: [0][K-1] coefficient form (after the inverse NTT), [0][i<L] NTT form
+  const u64 *c0_in;   // [items][L][N] NTT form
+  u64 *c0_out;        // [items][L][N]
+  const u32 *perm;    // NTT-slot permutation of the Galois element
+  const u64 *D;       // [items][L][N]
+  u64 *sum;           // [items][2][L][N], component 0 updated
+  const DevConsts *C;
+  TwRef tw;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    const int L = C->L, K = C->K, i = bid % L;
+    const size_t item = bid / L;
+    const DevMod mi = C->mod[i], msp = C->mod[K - 1];
+    const u64 q = mi.q;
+    const u64 *sp = acc + ((item * 2) * K + (K - 1)) * S;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[i], qi = C->qinvf[i];
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) {
+        const u64 r = csub(sp[j] + C->half_sp, msp.q);
+        const u64 ri = msp.q > q ? barrett64(r, mi) : r;
+        fm[pidx(j)] = u_to_f(sub_mod(ri, C->half_sp_mod_q[i], q));
+      }
+    }
+    SYNC();
+    ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
+    const u64 *a0 = acc + ((item * 2) * K + i) * S;
+    const u64 *cin = c0_in + (item * L + i) * S;
+    u64 *cout = c0_out + (item * L + i) * S;
+    const u64 *d = D + (item * L + i) * S;
+    u64 *s0 = sum + (item * 2 * L + i) * S;
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) {
+        const u64 t = f_canonical(fm[pidx(j)], qd, qi);
+        const u64 k0 = mul_shoup(sub_mod(a0[j], t, q), C->inv_sp_mod_q[i], q);
+        const u64 c = add_mod(cin[perm[j]], k0, q);
+        cout[j] = c;
+        s0[j] = add_mod(s0[j], mul_mod(c, d[j], mi), q);
       }
     }
   }
