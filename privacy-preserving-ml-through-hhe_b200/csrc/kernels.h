@@ -140,7 +140,18 @@ struct KsDigitsBody {
         const u64 *rn = reuse + static_cast<size_t>(b) * reuse_stride + static_cast<size_t>(J) * N;
         const u32 *pm = perm + static_cast<size_t>(h) * S;
         FOR_THREADS(tid, nt) {
-          for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(rn[pm[i]]);
+          constexpr int U = 4;
+          for (int i0 = tid; i0 < S; i0 += nt * U) {
+            u32 pj[U];
+            u64 rv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) pj[u] = pm[i0 + u * nt < S ? i0 + u * nt : i0];
+#pragma unroll
+            for (int u = 0; u < U; ++u) rv[u] = rn[pj[u]];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (i0 + u * nt < S) fm[pidx(i0 + u * nt)] = u_to_f(rv[u]);
+          }
         }
         SYNC();
       } else if (kFold) {
@@ -858,12 +869,31 @@ struct Corr0MacBody {
     const u64 *d = D + (item * L + i) * S;
     u64 *s0 = sum + (item * 2 * L + i) * S;
     FOR_THREADS(tid, nt) {
-      for (int j = tid; j < S; j += nt) {
-        const u64 t = f_canonical(fm[pidx(j)], qd, qi);
-        const u64 k0 = mul_shoup(sub_mod(a0[j], t, q), C->inv_sp_mod_q[i], q);
-        const u64 c = add_mod(cin[perm[j]], k0, q);
-        cout[j] = c;
-        s0[j] = add_mod(s0[j], mul_mod(c, d[j], mi), q);
+      constexpr int U = 4;  // independent gathers in flight per thread (perm -> c0 is a dependent pair of loads)
+      for (int j0 = tid; j0 < S; j0 += nt * U) {
+        u32 pj[U];
+        u64 cv[U], av[U], dv[U], sv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pj[u] = perm[j0 + u * nt < S ? j0 + u * nt : j0];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt < S ? j0 + u * nt : j0;
+          cv[u] = cin[pj[u]];
+          av[u] = a0[j];
+          dv[u] = d[j];
+          sv[u] = s0[j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt;
+          if (j < S) {
+            const u64 t = f_canonical(fm[pidx(j)], qd, qi);
+            const u64 k0 = mul_shoup(sub_mod(av[u], t, q), C->inv_sp_mod_q[i], q);
+            const u64 c = add_mod(cv[u], k0, q);
+            cout[j] = c;
+            s0[j] = add_mod(sv[u], mul_mod(c, dv[u], mi), q);
+          }
+        }
       }
     }
   }
