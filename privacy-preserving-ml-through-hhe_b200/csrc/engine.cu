@@ -28,7 +28,7 @@ bool getenv_flag(const char *name) {
 
 TabMap map_mod(int limbs, int period, int base) {
   TabMap m{};
-  for (int l = 0; l < limbs && l < kMaxTab; ++l) m.id[l] = static_cast<unsigned char>(base + (l % period));
+  for (int l = 0; l < limbs && l < kMaxMapLimbs; ++l) m.id[l] = static_cast<unsigned char>(base + (l % period));
   return m;
 }
 
@@ -54,8 +54,11 @@ u32 inv_mod_2n(u32 elt, u64 two_n) {
   }
 
 Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(device) {
-  if (P_.logn < 9 || P_.logn > 14)
-    throw std::invalid_argument("poly_modulus_degree must be in [512, 16384] for this engine build");
+  if (P_.logn < 9 || P_.logn > 15) throw std::invalid_argument("poly_modulus_degree must be in [512, 32768]");
+  // N = 32768: a limb does not fit one SM's shared memory -> split transforms (kernels.h NttSplitBody / KsDigitsQuadBody).
+  // HHE_FORCE_SPLIT=1 selects the same code path at smaller N (tests).
+  split_ = P_.logn == 15 || getenv_flag("HHE_FORCE_SPLIT");
+  if (split_ && table_is_f64(P_, 0)) throw std::invalid_argument("HHE_FORCE_SPLIT needs integer-path moduli (> 2^49)");
 #ifdef HHE_CUDA
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("NO_DEVICE: no CUDA device is visible (there is no CPU path)");
@@ -196,10 +199,35 @@ const W2 *Engine::need_key(int kind, u32 elt) const {
 
 // ------------------------------------------------------------------------------------------------ primitives
 void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride) {
+  if (split_) {
+    const size_t stride = item_stride ? item_stride : static_cast<size_t>(limbs) * P_.N;
+    Scope sc(*this);
+    if (!inverse && in == out) {
+      // both half-CTAs of a limb read the whole limb: an in-place forward transform needs a private copy of the input
+      const size_t words = (items - 1) * stride + static_cast<size_t>(limbs) * P_.N;
+      u64 *copy = scratch(words);
+      dev_.d2d(copy, in, words * 8);
+      in = copy;
+    }
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      NttSplitBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, stride};
+      dev_.launch(body, items * limbs * 2, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    if (inverse) {
+      const size_t total = items * limbs * (P_.N / 2);
+      InvFinalBody fin{out, dC_, twref(), map, limbs, stride, total};
+      dev_.launch(fin, ew_grid(total), kEwThreads, 0);
+    }
+    return;
+  }
   HHE_DISPATCH_LOG(P_.logn, {
     NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, item_stride ? item_stride : static_cast<size_t>(limbs) << LOGV};
     dev_.launch(body, items * limbs, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
+}
+
+void Engine::require_whole_limb(const char *what) const {
+  if (split_) throw std::invalid_argument(std::string(what) + " is not available at poly_modulus_degree 32768 in this build (NTT, rotate, relinearize, multiply are)");
 }
 
 void Engine::add(const u64 *a, const u64 *b, u64 *out, size_t items, int size) {
@@ -227,6 +255,7 @@ void Engine::broadcast(const u64 *src, u64 *out, size_t words, size_t items) {
 
 void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items) {
   if (n > P_.N) throw std::invalid_argument("values_matrix size exceeds slot count");
+  require_whole_limb("encode");
   HHE_DISPATCH_LOG(P_.logn, {
     EncodeBody<LOGV> body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, twref(), kSlots, 0, 0};
     dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -234,6 +263,7 @@ void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32
 }
 
 void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items) {
+  require_whole_limb("PASTA transciphering");
   HHE_DISPATCH_LOG(P_.logn, {
     EncodeBody<LOGV> body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, twref(), mode, layer, diag};
     dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -241,6 +271,7 @@ void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode
 }
 
 void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
+  require_whole_limb("multiply_plain");
   HHE_DISPATCH_LOG(P_.logn, {
     LiftNttBody<LOGV> body{pt, D, dC_, twref()};
     dev_.launch(body, items * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -249,6 +280,7 @@ void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
 
 void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps, size_t sum_off,
                      u64 *ntt_out) {
+  require_whole_limb("multiply_plain");
   HHE_DISPATCH_LOG(P_.logn, {
     NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out};
     dev_.launch(body, items * comps * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -307,11 +339,19 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
   Scope sc(*this);
   const int K = P_.K;
   u64 *acc = scratch(items * 2 * K * P_.N);
-  HHE_DISPATCH_LOG(P_.logn - 1, {
-    constexpr int S = 1 << LOGV;
-    KsDigitsBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items), nullptr, 0, nullptr};
-    dev_.launch(body, items * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
-  });
+  if (split_) {
+    HHE_DISPATCH_LOG(P_.logn - 2, {
+      constexpr int S = 1 << LOGV;
+      KsDigitsQuadBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items)};
+      dev_.launch(body, items * K * 4, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
+    });
+  } else {
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      constexpr int S = 1 << LOGV;
+      KsDigitsBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items), nullptr, 0, nullptr};
+      dev_.launch(body, items * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
+    });
+  }
   ntt(acc, acc, items, 2 * K, map_mod(2 * K, K, 0), true);
   ModDownBody md{acc, base0, base1, bstride, out, dC_, items * P_.N};
   dev_.launch(md, ew_grid(items * P_.N), kEwThreads, 0);

@@ -88,6 +88,7 @@ class Engine {
   void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb);
   void feistel(u64 *state, size_t nb);
   const W2 *need_key(int kind, u32 elt) const;
+  void require_whole_limb(const char *what) const;
   const u64 *feistel_mask_ntt();
 
   Params P_;
@@ -95,6 +96,7 @@ class Engine {
   int device_ = 0;
   int batch_ = 0;
   int f64_gmin_ = 1;
+  bool split_ = false;         // N = 32768 code path (split transforms)
   bool compact_keys_ = false;  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)
   DevConsts *dC_ = nullptr;
   W2 *dTw_ = nullptr;

@@ -24,8 +24,9 @@ struct TwRef {
   }
 };
 
+constexpr int kMaxMapLimbs = 3 * kMaxLimbs;  // size-3 ciphertext in the Bsk base
 struct TabMap {  // limb index inside an item -> NTT table id
-  unsigned char id[kMaxTab];
+  unsigned char id[kMaxMapLimbs];
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -313,6 +314,165 @@ struct KsDigitsBody {
       SYNC();
     }
     u64 *o0 = acc + ((static_cast<size_t>(b) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+    u64 *o1 = o0 + static_cast<size_t>(K) * N;
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) {
+        o0[i] = barrett64(acc0[i], mk);
+        o1[i] = barrett64(acc1[i], mk);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// N = 32768: a limb (256 KiB) no longer fits one SM's shared memory. Transforms are split in two N/2-point
+// sub-transforms (one CTA each): forward folds the first Cooley-Tukey stage into the load; inverse leaves the last
+// Gentleman-Sande stage (and the 1/N scaling) to InvFinalBody. Integer (wide-slack / Harvey) arithmetic only: the
+// BFVDefault(32768) primes are 55-56 bits.
+template <int LOGS>  // S = 2^LOGS = N/2
+struct NttSplitBody {
+  static constexpr const char *kName = "ntt_split";
+  const u64 *in;
+  u64 *out;
+  const DevConsts *C;
+  TwRef tw;
+  TabMap map;
+  int limbs;
+  int inverse;
+  size_t istride;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    const int h = bid & 1, lb = bid >> 1;
+    const int tab = map.id[lb % limbs];
+    const DevMod mm = C->mod[tab];
+    const u64 q = mm.q;
+    const size_t at = static_cast<size_t>(lb / limbs) * istride + static_cast<size_t>(lb % limbs) * (2 * S);
+    const u64 *src = in + at;
+    u64 *dst = out + at + static_cast<size_t>(h) * S;
+    if (!inverse) {
+      const W2 w1 = tw.fwd(tab)[1];
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) {
+          const u64 x = src[i], t = mul_shoup_lazy(src[i + S], w1.w, w1.ws, q);  // x < q, t < 2q
+          sm[pidx(i)] = h ? x + (q << 1) - t : x + t;                            // < 3q
+        }
+      }
+      SYNC();
+      ntt_fwd_core<LOGS>(sm, tw.fwd(tab), q, 2 + h, nt);
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) dst[i] = barrett64(sm[pidx(i)], mm);
+      }
+    } else {
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) sm[pidx(i)] = src[static_cast<size_t>(h) * S + i];
+      }
+      SYNC();
+      ntt_inv_core<LOGS>(sm, tw.inv(tab), q, 2 + h, nt);
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) dst[i] = sm[pidx(i)];  // lazy, < 2q; finished by InvFinalBody
+      }
+    }
+  }
+};
+
+// last Gentleman-Sande stage of the split inverse transform + 1/N: (a, b) = (d[j], d[j + N/2]) -> ((a+b)/N, (a-b) w^-1 / N)
+struct InvFinalBody {
+  static constexpr const char *kName = "ntt_inv_final";
+  u64 *data;
+  const DevConsts *C;
+  TwRef tw;
+  TabMap map;
+  int limbs;
+  size_t istride;
+  size_t total;  // items * limbs * N/2
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t half = C->N >> 1;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t lb = g / half, j = g % half;
+        const int tab = map.id[lb % limbs];
+        const u64 q = C->mod[tab].q, two_q = q << 1;
+        u64 *d = data + (lb / limbs) * istride + (lb % limbs) * (2 * half);
+        const W2 w = tw.inv(tab)[1], ninv = C->n_inv[tab];
+        const u64 a = d[j], b = d[j + half];  // both < 2q
+        const u64 s = csub(a + b, two_q);
+        const u64 t = mul_shoup_lazy(a + two_q - b, w.w, w.ws, q);
+        d[j] = mul_shoup(s, ninv, q);
+        d[j + half] = mul_shoup(t, ninv, q);
+      }
+    }
+  }
+};
+
+// Key-switch digit kernel for N = 32768: quarter split (two Cooley-Tukey stages folded into the digit load: 3 Shoup
+// products per residue instead of 1, but work buffer + accumulators fit: 68 + 128 KiB). CTA per (item, key limb, quarter).
+template <int LOGQ>  // S = 2^LOGQ = N/4
+struct KsDigitsQuadBody {
+  static constexpr const char *kName = "ks_digits_quad";
+  const u64 *target;
+  size_t stride;
+  const W2 *key;  // [L][2][K][N]
+  u64 *acc;       // [count][2][K][N]
+  const DevConsts *C;
+  TwRef tw;
+  int count;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGQ;
+    const int N = 4 * S;
+    const int K = C->K, L = C->L;
+    const int b = bid / (4 * K);
+    const int kc = bid % (4 * K);
+    const int k = kc >> 2, chunk = kc & 3, c1 = chunk >> 1, c0 = chunk & 1;
+    u64 *sm = reinterpret_cast<u64 *>(smem);
+    u64 *acc0 = sm + ntt_smem_words(S);
+    u64 *acc1 = acc0 + S;
+    const DevMod mk = C->mod[k];
+    const u64 q = mk.q, two_q = q << 1;
+    const W2 *twk = tw.fwd(k);
+    const W2 w1 = twk[1], w2 = twk[2 + c1];
+    FOR_THREADS(tid, nt) {
+      for (int i = tid; i < S; i += nt) acc0[i] = acc1[i] = 0;
+    }
+    for (int J = 0; J < L; ++J) {
+      const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
+      const bool reduce = C->mod[J].q > q;
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) {
+          // residues i, i + N/4 (this half of stage 0 pairs them with i + N/2, i + 3N/4)
+          u64 x0 = dig[i], x1 = dig[i + S], x2 = dig[i + 2 * S], x3 = dig[i + 3 * S];
+          if (reduce) {
+            x0 = barrett64(x0, mk);
+            x1 = barrett64(x1, mk);
+            x2 = barrett64(x2, mk);
+            x3 = barrett64(x3, mk);
+          }
+          const u64 t0 = mul_shoup_lazy(x2, w1.w, w1.ws, q), t1 = mul_shoup_lazy(x3, w1.w, w1.ws, q);
+          const u64 u0 = c1 ? x0 + two_q - t0 : x0 + t0;  // < 3q
+          const u64 u1 = c1 ? x1 + two_q - t1 : x1 + t1;
+          const u64 tt = mul_shoup_lazy(u1, w2.w, w2.ws, q);
+          const u64 u0r = csub(u0, two_q);                // < 2q
+          sm[pidx(i)] = c0 ? u0r + two_q - tt : u0r + tt;  // < 4q
+        }
+      }
+      SYNC();
+      ntt_fwd_core<LOGQ>(sm, twk, q, 4 + chunk, nt);
+      const W2 *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(chunk) * S;
+      const W2 *k1 = k0 + static_cast<size_t>(K) * N;
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) {
+          const u64 v = sm[pidx(i)];
+          const W2 a = k0[i], c = k1[i];
+          u64 s0 = acc0[i] + mul_shoup_lazy(v, a.w, a.ws, q);
+          u64 s1 = acc1[i] + mul_shoup_lazy(v, c.w, c.ws, q);
+          acc0[i] = s0 >= two_q ? s0 - two_q : s0;
+          acc1[i] = s1 >= two_q ? s1 - two_q : s1;
+        }
+      }
+      SYNC();
+    }
+    u64 *o0 = acc + ((static_cast<size_t>(b) * 2 + 0) * K + k) * N + static_cast<size_t>(chunk) * S;
     u64 *o1 = o0 + static_cast<size_t>(K) * N;
     FOR_THREADS(tid, nt) {
       for (int i = tid; i < S; i += nt) {

@@ -304,3 +304,35 @@ def test_n2048_fold_schedule(backend):
     assert np.array_equal(ctx.ntt(1, x), orc.ntt(1, x)) and np.array_equal(ctx.ntt(1, x, inverse=True), orc.ntt(1, x, inverse=True))
     ctx.close()
     orc.close()
+
+
+# ---- the N = 32768 code path (split transforms, quarter-split key switch), forced at N = 1024 so the oracle can check it
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_split_path_forced(backend, monkeypatch):
+    q = common.small_params(N, 3, 50)
+    orc = O.Oracle(N, common.T, q)
+    keys = ToyKeys(orc, 9)
+    monkeypatch.setenv("HHE_FORCE_SPLIT", "1")
+    ctx = make_ctx(backend, N, q)
+    monkeypatch.delenv("HHE_FORCE_SPLIT")
+    e1 = orc.galois_elt(-1)
+    for kind, elt, k in ((0, e1, keys.galois_key(e1)), (2, 0, keys.relin_key())):
+        orc.load_ksk(kind, elt, k)
+        ctx.load_ksk(kind, elt, k)
+    rng = np.random.default_rng(4)
+    for limb in range(2 * orc.K):
+        mod = int(orc.q[limb]) if limb < orc.K else int(orc.behz()["base_B"][limb - orc.K]) if limb - orc.K < orc.L else orc.behz()["m_sk"]
+        x = rng.integers(0, mod, (2, N), dtype=np.uint64)
+        f = ctx.ntt(limb, x)
+        assert np.array_equal(f, np.stack([orc.ntt(limb, v) for v in x])), limb
+        assert np.array_equal(ctx.ntt(limb, f, inverse=True), x), limb
+    a = keys.encrypt_zero_plus(orc, orc.encode(rng.integers(0, common.T, N, dtype=np.uint64)))
+    b = keys.encrypt_zero_plus(orc, orc.encode(rng.integers(0, common.T, N, dtype=np.uint64)))
+    assert np.array_equal(ctx.rotate_rows(a, -1), orc.rotate_rows(a, -1))
+    m3 = orc.multiply(a, b)
+    assert np.array_equal(ctx.multiply(a, b), m3)
+    assert np.array_equal(ctx.relinearize(m3), orc.relinearize(m3))
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.encode(np.arange(8, dtype=np.uint64))  # whole-limb kernels are not available on this path yet
+    ctx.close()
+    orc.close()

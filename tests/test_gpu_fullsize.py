@@ -87,3 +87,28 @@ def test_batch_and_counter_invariance(world):
         slots, _ = ref.decrypt(full[b])
         n = min(128, len(pt) - b * 128)
         assert np.array_equal(slots[:n], pt[b * 128:b * 128 + n])
+
+
+def test_n32768_primitives_bit_exact_with_seal():
+    """BASELINE.json configs[4] (primitive sweep) at N=32768, BFVDefault (L=15 + special): NTT, rotate, relinearize, multiply."""
+    NN = 32768
+    ref = R.Ref(NN, common.T, None, seed=6, steps=(-1,), default_gk=False)
+    ctx = pkg.Context(NN, common.T, ref.q, device=0)
+    assert ctx.info()["L"] == 15 and ctx.info()["fp64_moduli"] == 0
+    c, rb = ctx.constants(), ref.behz()
+    assert np.array_equal(c["psi"], ref.ntt_roots()[0]) and np.array_equal(c["base_B"], rb["base_B"])
+    common.load_keys_from_ref(ctx, ref, keysets=(0,))
+    rng = np.random.default_rng(12)
+    for limb in (0, 7, ref.K - 1):
+        x = rng.integers(0, int(ref.q[limb]), NN, dtype=np.uint64)
+        f = ctx.ntt(limb, x)
+        assert np.array_equal(f, ref.ntt(limb, x))
+        assert np.array_equal(ctx.ntt(limb, f, inverse=True), x)
+    a = ref.encrypt(rng.integers(0, common.T, NN, dtype=np.uint64))
+    b = ref.encrypt(rng.integers(0, common.T, NN, dtype=np.uint64))
+    assert np.array_equal(ctx.rotate_rows(a, -1), ref.rotate_rows(a, -1))
+    m3 = ref.multiply(a, b)
+    assert np.array_equal(ctx.multiply(a, b), m3)
+    assert np.array_equal(ctx.relinearize(m3), ref.relinearize(m3))
+    ctx.close()
+    ref.close()
