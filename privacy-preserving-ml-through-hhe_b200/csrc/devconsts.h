@@ -65,7 +65,7 @@ inline bool table_is_f64(const Params &p, int tab) {
 #else
   if (tab >= p.K || p.L > 8) return false;
   for (int i = 0; i < p.K; ++i)
-    if (p.q[i] > kF64ModLimit) return false;
+    if (p.q[i] >= kF64ModLimit) return false;
   return true;
 #endif
 }

@@ -175,17 +175,17 @@ struct KsDigitsBody {
               const int i = i0 + u * nt;
               if (i < S / 2) {
                 const double t0 = f_mulmod_const(u_to_f(v[u][1]), w1, q), t1 = f_mulmod_const(u_to_f(v[u][3]), w1, q);
-                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);  // |.| <= 3.5q
+                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);  // |.| <= 3q
                 const double a1 = h ? f_add(u_to_f(v[u][2]), -t1) : f_add(u_to_f(v[u][2]), t1);
                 const double tt = f_mulmod_const(a1, w2, q);
-                fm[pidx(i)] = f_add(a0, tt);  // |.| <= 5q
+                fm[pidx(i)] = f_add(a0, tt);  // |.| <= 4q
                 fm[pidx(i + S / 2)] = f_add(a0, -tt);
               }
             }
           }
         }
         SYNC();
-        ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), 10>(fm, twk, q, qi, h, nt);
+        ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), 8>(fm, twk, q, qi, h, nt);
       } else {
         FOR_THREADS(tid, nt) {
           constexpr int U = 4;
@@ -202,13 +202,13 @@ struct KsDigitsBody {
               const int i = i0 + u * nt;
               if (i < S) {
                 const double t = f_mulmod_const(u_to_f(ys[u]), w1, q);
-                fm[pidx(i)] = h ? f_add(u_to_f(xs[u]), -t) : f_add(u_to_f(xs[u]), t);  // |.| <= 3.5q
+                fm[pidx(i)] = h ? f_add(u_to_f(xs[u]), -t) : f_add(u_to_f(xs[u]), t);  // |.| <= 3q
               }
             }
           }
         }
         SYNC();
-        ntt_fwd_core_f64<LOGH, 1, 7>(fm, twk, q, qi, h, nt);
+        ntt_fwd_core_f64<LOGH, 1, 6>(fm, twk, q, qi, h, nt);
       }
       // compact FP64 key: double[L][2][K][N] (8 bytes per residue; k/q is formed as k * (1/q))
       const double *k0 = reinterpret_cast<const double *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
@@ -218,7 +218,7 @@ struct KsDigitsBody {
         for (int i = tid; i < S; i += nt) {
           const double v = fm[pidx(i)];
           const double a = k0[i], c = k1[i];
-          // L <= 8 terms of magnitude <= 1.5q: |acc| <= 12q < 2^53, every partial sum is an exact integer
+          // L <= 8 terms of magnitude <= q: |acc| <= 8q <= 2^52, every partial sum is an exact integer
           acc0[i] = f_add(acc0[i], f_mulmod_const(v, D2{a, f_mul(a, qi)}, q));
           acc1[i] = f_add(acc1[i], f_mulmod_const(v, D2{c, f_mul(c, qi)}, q));
         }

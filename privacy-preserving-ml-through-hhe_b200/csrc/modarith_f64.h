@@ -5,11 +5,11 @@
 // DFMA at 16 lanes/clk per sub-partition (2 cycles per warp instruction) and is otherwise idle. A modular product
 // needs 6 FP64 instructions here, a butterfly 8.
 //
-// Representation: residues are doubles holding (signed) integers of magnitude < 8q <= 2^52, so every value, sum and
-// difference below is an exactly representable integer. All operations are written with explicit fma / mul / add
-// (no contraction) and are exact:
+// Representation: residues are doubles holding (signed) integers; every operand of a product has magnitude <= 4q < 2^51
+// and every sum stays below 2^53, so every value, sum and difference below is an exactly representable integer.
+// All operations are written with explicit fma / mul / add (no contraction) and are exact:
 //   h  = RN(b*w)            l = fma(b, w, -h) = b*w - h exactly (error-free product)
-//   qh = rint(b * winv)     winv = RN(w/q);  |b*w/q - qh| <= 1 for |b| < 2^52
+//   qh = rint(b * winv)     winv ~ w/q (relative error <= 2^-52);  |b*w/q - qh| <= 1 for |b| <= 4q < 2^51
 //   r  = fma(-qh, q, h)     exact: |h - qh*q| <= q + |l| < 2^51
 //   b*w mod q  ==  r + l    an integer of magnitude <= q
 // Only the final canonical residue in [0, q) leaves a kernel, so results are bit-identical with integer arithmetic.
@@ -20,11 +20,12 @@
 
 #if !defined(__CUDA_ARCH__)
 #include <cmath>
+#include <cstdlib>
 #endif
 
 namespace hhe {
 
-constexpr u64 kF64ModLimit = 1ULL << 49;  // q <= 2^49  =>  8q <= 2^52
+constexpr u64 kF64ModLimit = 1ULL << 49;  // q < 2^49  =>  4q < 2^51 (f_rint_mul), 8q <= 2^52 (key inner product)
 
 struct D2 {  // FP64 twiddle / key element: value and value/q
   double w, winv;
@@ -73,20 +74,24 @@ HD u64 double_to_bits(double d) {
 }
 
 constexpr u64 kTwo52Bits = 0x4330000000000000ULL;  // 2^52 as a bit pattern
-constexpr u64 kSignBit = 0x8000000000000000ULL;
 
 // unsigned integer < 2^52 -> double (exact): splice into the mantissa of 2^52, subtract 2^52
 HD double u_to_f(u64 x) { return f_add(bits_to_double(x | kTwo52Bits), -4503599627370496.0); }
 // double holding an integer in [0, 2^52) -> unsigned
 HD u64 f_to_u(double d) { return double_to_bits(f_add(d, 4503599627370496.0)) & ((1ULL << 52) - 1); }
 
-// round-to-nearest integer of x*y for |x*y| < 2^52: add and subtract 2^52 carrying the sign of x (y > 0)
+// round-to-nearest integer of x*y for |x*y| < 2^51: adding 1.5 * 2^52 moves the product into [2^52, 2^53) where the
+// spacing of doubles is 1, so the fused multiply-add itself rounds to an integer; subtracting the constant is exact.
+// (No sign handling, no extra registers: 2 FP64 instructions.) Every caller keeps |x| <= 4q < 2^51 and 0 <= y <= 1.
 HD double f_rint_mul(double x, double y) {
-  const double c = bits_to_double(kTwo52Bits | (double_to_bits(x) & kSignBit));
-  return f_add(f_fma(x, y, c), -c);
+  constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+#if defined(HHE_EMULATE)
+  if (!(std::fabs(x * y) < 2251799813685248.0)) std::abort();  // bound discipline check (test harness only)
+#endif
+  return f_add(f_fma(x, y, kMagic), -kMagic);
 }
 
-// b * w mod q for a precomputed constant (w, winv = w/q): result is an integer with |result| <= q, for |b| < 2^52
+// b * w mod q for a precomputed constant (w, winv ~ w/q): result is an integer with |result| <= q, for |b| <= 4q
 HD double f_mulmod_const(double b, D2 c, double q) {
   const double qh = f_rint_mul(b, c.winv);
   const double h = f_mul(b, c.w);
@@ -94,7 +99,7 @@ HD double f_mulmod_const(double b, D2 c, double q) {
   return f_add(f_fma(-qh, q, h), l);
 }
 
-// a * b mod q for two variable operands (|a| < 2^52, |b| <= q): quotient from h * (1/q); |result| <= 3q
+// a * b mod q for two variable operands (|a| <= 4q, 0 <= b < q): quotient from h * (1/q); |result| <= 2q
 HD double f_mulmod_var(double a, double b, double q, double qinv) {
   const double h = f_mul(a, b);
   const double l = f_fma(a, b, -h);
@@ -102,10 +107,10 @@ HD double f_mulmod_var(double a, double b, double q, double qinv) {
   return f_add(f_fma(-qh, q, h), l);
 }
 
-// x mod q into [-q/2 - 1, q/2 + 1] for |x| < 2^52
+// x mod q into [-q/2 - 1, q/2 + 1] for |x| < 2^53
 HD double f_reduce(double x, double q, double qinv) { return f_fma(-f_rint_mul(x, qinv), q, x); }
 
-// any |x| < 2^52 -> canonical residue in [0, q) as an unsigned integer
+// any |x| < 2^53 -> canonical residue in [0, q) as an unsigned integer
 HD u64 f_canonical(double x, double q, double qinv) {
   double r = f_reduce(x, q, qinv);
   if (r < 0.0) r = f_add(r, q);

@@ -163,11 +163,11 @@ HD void ntt_inv_core(u64 *sm, const W2 *__restrict__ tw, u64 q, u32 mc, int nt) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// FP64-pipe variants (q <= 2^49, see modarith_f64.h). Shared memory holds doubles (signed integers, |x| < 8q).
+// FP64-pipe variants (q <= 2^49, see modarith_f64.h). Shared memory holds doubles (signed integers, |x| <= 4q).
 //
-// Twiddles are plain doubles w (8 bytes); w/q is formed on the fly as w * (1/q) (one DMUL), which keeps the quotient
-// estimate within 1.5 of the true quotient, so |w*b mod q| <= 1.5 q: bounds below are in units of q, a forward stage
-// adds at most 1.5, an inverse stage doubles.
+// Twiddles are plain doubles w (8 bytes); w/q is formed on the fly as w * (1/q) (one DMUL, relative error <= 2^-52), which
+// keeps the quotient estimate within 1 of the true quotient for |b| <= 4q, so |w*b mod q| <= q: bounds below are in units
+// of q, a forward stage adds at most 1, an inverse stage doubles.
 //
 // Two table layouts per (modulus, direction), both of N doubles (F64Tw):
 //   idx[k]          index-major, SEAL's order (psi^bitrev(k)): used by passes whose twiddles are warp-uniform
@@ -255,13 +255,14 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   for (int e = 0; e < E; ++e) sm[a0 + off(e)] = x[e];
 }
 
-// Compile-time chain of forward passes. B2 = twice the bound (in units of q) of the values entering the pass; a pass
-// of R stages adds 1.5 R; values must stay below 8q at every stage input, i.e. the bound after the pass <= 7.5 q.
+// Compile-time chain of forward passes. B2 = twice the bound (in units of q) of the values entering the pass. A stage
+// adds at most q (|w*b mod q| <= q while |b| <= 4q), and every stage input must stay <= 4q (f_rint_mul), so a pass of R
+// stages may start from a bound of at most 4 - (R - 1); otherwise its values are reduced to q/2 on load.
 template <int LOGS, int LM, int S0, int B2>
 struct FwdChainF64 {
   static constexpr int R = S0 == 0 ? NttSchedule<LOGS>::kFirst : kRadixLog;
-  static constexpr bool kReduce = B2 + 3 * R > 15;
-  static constexpr int kOut = (kReduce ? 1 : B2) + 3 * R;
+  static constexpr bool kReduce = B2 + 2 * (R - 1) > 8;
+  static constexpr int kOut = (kReduce ? 1 : B2) + 2 * R;
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
     FOR_THREADS(tid, nt) {
       for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, false, LOGS, S0, LM>(sm, tw, q, qinv, chunk, g, kReduce);
@@ -272,7 +273,7 @@ struct FwdChainF64 {
   static HD void run_next(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) { run(sm, tw, q, qinv, chunk, nt); }
 };
 
-// Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues). Output < 8q.
+// Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues). Output <= 4q.
 template <int LOGS, int LM, int B2IN>
 HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
   static_assert(kRadixLog == 3, "FP64 path is written for radix-8 register passes");
@@ -285,7 +286,7 @@ HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int c
   FwdChainF64<LOGS, LM, S0, B2IN>::run(sm, tw, q, qinv, chunk, nt);
 }
 
-// Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2 = 4q < 8q).
+// Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2: differences stay <= 4q).
 template <int LOGS, int LM, int S0>
 struct InvChainF64 {
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
