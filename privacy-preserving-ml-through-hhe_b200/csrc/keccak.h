@@ -150,7 +150,6 @@ struct MaterialBody {
       }
       SYNC();
       for (int i = 1; i < T; ++i) {
-        u32 mine[1];
         // two-phase update through a second buffer so that the read of prev[j-1] never races the write of prev[j]
         u32 *next = prev + 2 * T + ((i & 1) ? 0 : 2 * T);
         const u32 *cur = (i == 1) ? prev : prev + 2 * T + ((i & 1) ? 2 * T : 0);
@@ -160,9 +159,8 @@ struct MaterialBody {
             const u32 *M = o + (static_cast<size_t>(layer) * 2 + m) * T * T;
             u64 v = static_cast<u64>(M[j]) * cur[m * T + T - 1] % p;
             if (j) v = (v + cur[m * T + j - 1]) % p;
-            mine[0] = static_cast<u32>(v);
-            next[tid] = mine[0];
-            o[(static_cast<size_t>(layer) * 2 + m) * T * T + static_cast<size_t>(i) * T + j] = mine[0];
+            next[tid] = static_cast<u32>(v);
+            o[(static_cast<size_t>(layer) * 2 + m) * T * T + static_cast<size_t>(i) * T + j] = static_cast<u32>(v);
           }
         }
         SYNC();

@@ -219,8 +219,6 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   if (!INVERSE) {
 #pragma unroll
     for (int d = 0; d < R; ++d) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const int half = E >> (d + 1);
 #pragma unroll
       for (int j = 0; j < (1 << d); ++j) {

@@ -336,3 +336,42 @@ def test_split_path_forced(backend, monkeypatch):
         ctx.encode(np.arange(8, dtype=np.uint64))  # whole-limb kernels are not available on this path yet
     ctx.close()
     orc.close()
+
+
+# ---- edge cases and error behaviour (the reference throws std::invalid_argument / std::logic_error here) -------------
+def test_edge_cases_and_errors(eng, world):
+    o, keys, cts = world["orc"], world["keys"], world["cts"]
+    ek = cts[0]
+    # empty input: zero blocks, no device work
+    assert eng.pasta3_decompose(ek, np.zeros(0, dtype=np.uint64)).shape[0] == 0
+    # a single word is one ragged block
+    one = eng.pasta3_decompose(ek, np.array([5], dtype=np.uint64))
+    assert np.array_equal(one, o.pasta_decompose(ek, np.array([5], dtype=np.uint64)))
+    # words must be residues mod t (BatchEncoder::encode would throw)
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.pasta3_decompose(ek, np.array([common.T], dtype=np.uint64))
+    # flatten of a single ciphertext is the identity; vec_sum(n=1) too
+    assert np.array_equal(eng.flatten(cts[:1]), cts[0])
+    assert np.array_equal(eng.vec_sum(cts[0], 1, 1), cts[0])
+    # wrong buffer sizes are rejected before anything is uploaded
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.add(cts[0][:1], cts[1][:1])
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.load_ksk(0, 3, np.zeros(10, dtype=np.uint64))
+    # all-zero mask: SEAL reports a transparent ciphertext
+    with pytest.raises(pkg.HheLogicError):
+        eng.mask(cts[0], np.zeros(4, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_missing_keys_raise(backend):
+    q = common.small_params(N, 2, 50)
+    ctx = make_ctx(backend, N, q)
+    ct = np.zeros((2, 2, N), dtype=np.uint64)
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.relinearize(np.zeros((3, 2, N), dtype=np.uint64))  # no relin key loaded
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.rotate_rows(ct, -1)  # "Galois key not present"
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.pasta3_decompose(ct, np.arange(4, dtype=np.uint64))  # PASTA needs steps -1, +128, columns and relin
+    ctx.close()
