@@ -7,6 +7,45 @@
 
 namespace hhe {
 
+// global-memory IO functors for the fused first / last register pass of the FP64 transforms (ntt_core.h: SmemIO)
+struct LoadU64 {  // canonical residues -> doubles
+  static constexpr bool kLoad = true, kStore = false;
+  const u64 *src;
+  HD double load(int i) const { return u_to_f(src[i]); }
+  HD void store(int, double) const {}
+};
+struct LoadLift {  // centred lift of a plaintext coefficient into the limb (Evaluator::multiply_plain)
+  static constexpr bool kLoad = true, kStore = false;
+  const u64 *src;
+  u64 thr, inc;
+  HD double load(int i) const {
+    const u64 m = src[i];
+    return u_to_f(m >= thr ? m + inc : m);
+  }
+  HD void store(int, double) const {}
+};
+struct StoreScaled {  // inverse transform output: multiply by N^-1, canonicalise, store
+  static constexpr bool kLoad = false, kStore = true;
+  u64 *dst;
+  D2 ninv;
+  double q, qinv;
+  HD double load(int) const { return 0.0; }
+  HD void store(int i, double v) const { dst[i] = f_canonical(f_mulmod_const(v, ninv, q), q, qinv); }
+};
+
+struct LoadCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[special] + half mod q_sp  (Corr0MacBody)
+  static constexpr bool kLoad = true, kStore = false;
+  const u64 *sp;
+  u64 half_sp, half_i, q;
+  DevMod mi, msp;
+  HD double load(int j) const {
+    const u64 r = csub(sp[j] + half_sp, msp.q);
+    const u64 ri = msp.q > q ? barrett64(r, mi) : r;
+    return u_to_f(sub_mod(ri, half_i, q));
+  }
+  HD void store(int, double) const {}
+};
+
 struct TwRef {
   const W2 *base;  // all tables
   u64 N;
@@ -54,21 +93,17 @@ struct NttBody {
     if (C->f64[tab]) {  // FP64-pipe transform (modarith_f64.h)
       double *fm = reinterpret_cast<double *>(smem);
       const double qd = C->qf[tab], qi = C->qinvf[tab];
-      FOR_THREADS(tid, nt) {
-        for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(src[i]);
-      }
-      SYNC();
       if (!inverse) {
-        ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(tab), qd, qi, 0, nt);
+        ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(tab), qd, qi, 0, nt, LoadU64{src});
         FOR_THREADS(tid, nt) {
           for (int i = tid; i < S; i += nt) dst[i] = f_canonical(fm[pidx(i)], qd, qi);
         }
       } else {
-        ntt_inv_core_f64<LOGS, 0>(fm, tw.inv_f(tab), qd, qi, 0, nt);
-        const D2 ninv = C->n_inv_f[tab];
         FOR_THREADS(tid, nt) {
-          for (int i = tid; i < S; i += nt) dst[i] = f_canonical(f_mulmod_const(fm[pidx(i)], ninv, qd), qd, qi);
+          for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(src[i]);
         }
+        SYNC();
+        ntt_inv_core_f64<LOGS, 0>(fm, tw.inv_f(tab), qd, qi, 0, nt, StoreScaled{dst, C->n_inv_f[tab], qd, qi});
       }
       return;
     }
@@ -735,14 +770,7 @@ struct LiftNttBody {
     if (C->f64[i]) {
       double *fm = reinterpret_cast<double *>(smem);
       const double qd = C->qf[i], qi = C->qinvf[i];
-      FOR_THREADS(tid, nt) {
-        for (int j = tid; j < S; j += nt) {
-          const u64 m = src[j];
-          fm[pidx(j)] = u_to_f(m >= thr ? m + inc : m);
-        }
-      }
-      SYNC();
-      ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
+      ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt, LoadLift{src, thr, inc});
       u64 *dstf = out + static_cast<size_t>(bid) * S;
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) dstf[j] = f_canonical(fm[pidx(j)], qd, qi);
@@ -797,11 +825,7 @@ struct NttMacBody {
     if (C->f64[i]) {
       double *fm = reinterpret_cast<double *>(smem);
       const double qd = C->qf[i], qi = C->qinvf[i];
-      FOR_THREADS(tid, nt) {
-        for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
-      }
-      SYNC();
-      ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
+      ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt, LoadU64{src});
       FOR_THREADS(tid, nt) {
         for (int j = tid; j < S; j += nt) {
           if (nout) nout[j] = f_canonical(fm[pidx(j)], qd, qi);
@@ -1014,15 +1038,7 @@ struct Corr0MacBody {
     const u64 *sp = acc + ((item * 2) * K + (K - 1)) * S;
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[i], qi = C->qinvf[i];
-    FOR_THREADS(tid, nt) {
-      for (int j = tid; j < S; j += nt) {
-        const u64 r = csub(sp[j] + C->half_sp, msp.q);
-        const u64 ri = msp.q > q ? barrett64(r, mi) : r;
-        fm[pidx(j)] = u_to_f(sub_mod(ri, C->half_sp_mod_q[i], q));
-      }
-    }
-    SYNC();
-    ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt);
+    ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(i), qd, qi, 0, nt, LoadCorr{sp, C->half_sp, C->half_sp_mod_q[i], q, mi, msp});
     const u64 *a0 = acc + ((item * 2) * K + i) * S;
     const u64 *cin = c0_in + (item * L + i) * S;
     u64 *cout = c0_out + (item * L + i) * S;

@@ -187,8 +187,18 @@ HD size_t f64tw_offset(int g0, int gmin) {
 
 // Register pass over local stages [S0, S0+R) of chunk `chunk` of a transform that was split into 2^LM chunks.
 // Every stride is a compile-time constant, so shared-memory and twiddle accesses use immediate offsets.
-template <int R, bool INVERSE, int LOGS, int S0, int LM>
-HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, bool reduce) {
+// IO: optional global-memory side of the pass. The forward transform's first pass (S0 == 0) can take its inputs from
+// IO::load(i) and the inverse transform's last pass (S0 == 0) can hand its outputs to IO::store(i, v) instead of going
+// through shared memory: in both, consecutive threads touch consecutive residues (coalesced), and one shared-memory
+// round trip plus one barrier per transform disappear.
+struct SmemIO {
+  static constexpr bool kLoad = false, kStore = false;
+  HD double load(int) const { return 0.0; }
+  HD void store(int, double) const {}
+};
+
+template <int R, bool INVERSE, int LOGS, int S0, int LM, class IO = SmemIO>
+HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, bool reduce, const IO &io = IO()) {
   constexpr int E = 1 << R;
   constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
   constexpr int G0 = S0 + LM;        // global stage of the pass
@@ -209,9 +219,11 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
       for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw.idx[(static_cast<size_t>(1) << (G0 + d)) + (static_cast<size_t>(H) << d) + j];
     }
   }
+  constexpr bool kGlobalIn = IO::kLoad && !INVERSE && S0 == 0;
+  constexpr bool kGlobalOut = IO::kStore && INVERSE && S0 == 0;
   double x[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) x[e] = sm[a0 + off(e)];
+  for (int e = 0; e < E; ++e) x[e] = kGlobalIn ? io.load((hi << (LOGS - S0)) + lo + (e << LG)) : sm[a0 + off(e)];
   if (reduce) {
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = f_reduce(x[e], q, qinv);
@@ -250,7 +262,12 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
     }
   }
 #pragma unroll
-  for (int e = 0; e < E; ++e) sm[a0 + off(e)] = x[e];
+  for (int e = 0; e < E; ++e) {
+    if (kGlobalOut)
+      io.store((hi << (LOGS - S0)) + lo + (e << LG), x[e]);
+    else
+      sm[a0 + off(e)] = x[e];
+  }
 }
 
 // Compile-time chain of forward passes. B2 = twice the bound (in units of q) of the values entering the pass. A stage
@@ -261,21 +278,21 @@ struct FwdChainF64 {
   static constexpr int R = S0 == 0 ? NttSchedule<LOGS>::kFirst : kRadixLog;
   static constexpr bool kReduce = B2 + 2 * (R - 1) > 8;
   static constexpr int kOut = (kReduce ? 1 : B2) + 2 * R;
-  static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+  template <class IO = SmemIO>
+  static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, false, LOGS, S0, LM>(sm, tw, q, qinv, chunk, g, kReduce);
+      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, false, LOGS, S0, LM, IO>(sm, tw, q, qinv, chunk, g, kReduce, io);
     }
     SYNC();
-    if (S0 + R < LOGS) FwdChainF64<LOGS, LM, (S0 + R < LOGS ? S0 + R : 0), (S0 + R < LOGS ? kOut : 0)>::run_next(sm, tw, q, qinv, chunk, nt);
+    if (S0 + R < LOGS) FwdChainF64<LOGS, LM, (S0 + R < LOGS ? S0 + R : 0), (S0 + R < LOGS ? kOut : 0)>::run(sm, tw, q, qinv, chunk, nt);
   }
-  static HD void run_next(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) { run(sm, tw, q, qinv, chunk, nt); }
 };
 
 // Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues). Output <= 4q.
-template <int LOGS, int LM, int B2IN>
-HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+template <int LOGS, int LM, int B2IN, class IO = SmemIO>
+HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
   static_assert(kRadixLog == 3, "FP64 path is written for radix-8 register passes");
-  FwdChainF64<LOGS, LM, 0, B2IN>::run(sm, tw, q, qinv, chunk, nt);
+  FwdChainF64<LOGS, LM, 0, B2IN>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 // Same, entering the chain at local stage S0 (the caller already performed the stages below S0).
@@ -287,21 +304,24 @@ HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int c
 // Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2: differences stay <= 4q).
 template <int LOGS, int LM, int S0>
 struct InvChainF64 {
-  static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+  template <class IO = SmemIO>
+  static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
     constexpr int R0 = NttSchedule<LOGS>::kFirst;
     constexpr int R = S0 == 0 ? R0 : kRadixLog;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, true, LOGS, S0, LM>(sm, tw, q, qinv, chunk, g, true);
+      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, true, LOGS, S0, LM, IO>(sm, tw, q, qinv, chunk, g, true, io);
     }
     SYNC();
-    if (S0 > 0) InvChainF64<LOGS, LM, (S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt);
+    if (S0 > 0) InvChainF64<LOGS, LM, (S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
-template <int LOGS, int LM>
-HD void ntt_inv_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
+// Inverse transform on doubles (without 1/N unless the IO functor applies it). With a storing IO functor the results
+// leave through IO::store and shared memory holds garbage afterwards.
+template <int LOGS, int LM, class IO = SmemIO>
+HD void ntt_inv_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
   constexpr int R0 = NttSchedule<LOGS>::kFirst;
-  InvChainF64<LOGS, LM, (LOGS - kRadixLog >= R0 ? LOGS - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt);
+  InvChainF64<LOGS, LM, (LOGS - kRadixLog >= R0 ? LOGS - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 }  // namespace hhe
