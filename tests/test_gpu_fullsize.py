@@ -112,3 +112,34 @@ def test_n32768_primitives_bit_exact_with_seal():
     assert np.array_equal(ctx.relinearize(m3), ref.relinearize(m3))
     ctx.close()
     ref.close()
+
+
+def test_n8192_primitives_bit_exact_with_seal():
+    """BASELINE.json configs[4] at N=8192, BFVDefault (L=4 + special, 43/44-bit primes: FP64-pipe kernels)."""
+    NN = 8192
+    ref = R.Ref(NN, common.T, None, seed=8, steps=(0, -1, 128), default_gk=False)
+    assert list(ref.q) == common.Q_8192
+    ctx = pkg.Context(NN, common.T, ref.q, device=0)
+    assert ctx.info()["fp64_moduli"] == 5
+    common.load_keys_from_ref(ctx, ref, keysets=(0,))
+    rng = np.random.default_rng(13)
+    for limb in range(ref.K):
+        x = rng.integers(0, int(ref.q[limb]), NN, dtype=np.uint64)
+        f = ctx.ntt(limb, x)
+        assert np.array_equal(f, ref.ntt(limb, x)) and np.array_equal(ctx.ntt(limb, f, inverse=True), x)
+    a = ref.encrypt(rng.integers(0, common.T, NN, dtype=np.uint64))
+    b = ref.encrypt(rng.integers(0, common.T, NN, dtype=np.uint64))
+    pt = ref.encode(rng.integers(0, common.T, 5000, dtype=np.uint64))
+    assert np.array_equal(ctx.multiply_plain(a, pt), ref.multiply_plain(a, pt))
+    assert np.array_equal(ctx.rotate_rows(a, -1), ref.rotate_rows(a, -1))
+    assert np.array_equal(ctx.rotate_columns(a), ref.rotate_columns(a))
+    m3 = ref.multiply(a, b)
+    assert np.array_equal(ctx.multiply(a, b), m3)
+    assert np.array_equal(ctx.relinearize(m3), ref.relinearize(m3))
+    # the whole PASTA pipeline runs at this ring too (the noise budget is exhausted, limbs must still match)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    ek = ref.encrypt(common.pack_key(key, NN))
+    sym = rng.integers(0, common.T, 128, dtype=np.uint64)
+    assert np.array_equal(ctx.pasta3_decompose(ek, sym), ref.pasta_decompose(ek, sym, False))
+    ctx.close()
+    ref.close()
