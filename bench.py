@@ -295,16 +295,20 @@ def main():
     ks = prof.get("ks_digits", {"launches": 0, "ms": 0.0})
     avg_ms = ks["ms"] / max(1, ks["launches"])
     achieved = KS_BYTES * B / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
-    traffic = None
+    traffic, ncu = None, None
     tpath = os.path.join(ROOT, "profiles", "ks_digits_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch_at_bench_batch")
+        ncu = json.load(open(tpath))
+        # the capture ran at 148 items per launch; DRAM traffic scales with the items of a launch
+        traffic = int(ncu["dram_bytes_per_launch_at_capture_batch_148"] * B / 148)
     kernel_ms = sum(v["ms"] for v in prof.values())
     roofline = {
         "bound": "hbm", "kernel": "ks_digits (key-switch digit NTT + key inner product)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": KS_BYTES * B, "avg_launch_ms": avg_ms, "launches": ks["launches"],
         "share_of_kernel_time": ks["ms"] / kernel_ms if kernel_ms else None, "dominant_by_time": dom[0],
+        "ncu": ({k: ncu[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "lsu_wavefront_pipe_pct", "dram_throughput_pct", "source")}
+                if ncu else None),
         "note": "exact 64-bit modular arithmetic: bounded by instruction issue / the FP64 and IMAD pipes, not HBM (see DESIGN.md, profiles/)",
         "step_level": {"algorithmic_bytes_per_block": BYTES_PER_BLOCK[bool(args.bsgs)],
                        "achieved": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9,
