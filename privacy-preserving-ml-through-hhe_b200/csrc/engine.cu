@@ -87,6 +87,7 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   f64_gmin_ = P_.logn % 3 ? P_.logn % 3 : 3;
   compact_keys_ = true;
   for (int k = 0; k < P_.K; ++k) compact_keys_ = compact_keys_ && table_is_f64(P_, k);
+  tmem_ks_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_TMEM");
   std::vector<W2> tw(ntab * 2 * P_.N);
   for (size_t t = 0; t < ntab; ++t) {
     if (!P_.tab[t].q) continue;
@@ -177,7 +178,7 @@ void Engine::load_ksk(int kind, u32 elt, const u64 *host_ksk) {
   u64 *raw = scratch(words);
   dev_.h2d(raw, host_ksk, words * 8);
   W2 *dst = static_cast<W2 *>(dev_.dmalloc(words * (compact_keys_ ? sizeof(double) : sizeof(W2))));
-  ShoupifyBody body{raw, dst, dC_, words, compact_keys_ ? 1 : 0};
+  ShoupifyBody body{raw, dst, dC_, words, compact_keys_ ? 1 : 0, tmem_ks_ ? 1 : 0};
   dev_.launch(body, ew_grid(words), kEwThreads, 0);
   dev_.sync();  // host_ksk may be released by the caller; raw scratch is recycled
   auto key = std::make_pair(kind, elt);
@@ -346,15 +347,36 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
       dev_.launch(body, items * K * 4, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
     });
   } else {
-    HHE_DISPATCH_LOG(P_.logn - 1, {
-      constexpr int S = 1 << LOGV;
-      KsDigitsBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items), nullptr, 0, nullptr};
-      dev_.launch(body, items * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
-    });
+    launch_ks_digits(target, tstride, key, acc, items, nullptr, 0, nullptr);
   }
   ntt(acc, acc, items, 2 * K, map_mod(2 * K, K, 0), true);
   ModDownBody md{acc, base0, base1, bstride, out, dC_, items * P_.N};
   dev_.launch(md, ew_grid(items * P_.N), kEwThreads, 0);
+}
+
+void Engine::launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, u64 *acc, size_t items, const u64 *reuse,
+                              size_t reuse_stride, const u32 *perm) {
+  const int K = P_.K;
+  if (tmem_ks_) {
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      constexpr int G = (1 << LOGV) / 8;
+      const int nt = std::max(32, std::min(512, G));
+#ifdef HHE_CUDA
+      const bool emulate = false;
+#else
+      const bool emulate = true;
+#endif
+      KsDigitsTmemBody<LOGV> body{target, tstride, reinterpret_cast<const double *>(key), acc, dC_, twref(), static_cast<int>(items),
+                                  reuse, reuse_stride, perm};
+      dev_.launch(body, items * K * 2, nt, KsDigitsTmemBody<LOGV>::smem_bytes(nt, emulate));
+    });
+    return;
+  }
+  HHE_DISPATCH_LOG(P_.logn - 1, {
+    constexpr int S = 1 << LOGV;
+    KsDigitsBody<LOGV> body{target, tstride, key, acc, dC_, twref(), static_cast<int>(items), reuse, reuse_stride, perm};
+    dev_.launch(body, items * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
+  });
 }
 
 void Engine::apply_galois(const u64 *a, u32 elt, const W2 *key, u64 *out, size_t items) {
@@ -526,11 +548,7 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
       GaloisBody gb{c1c, g1, dC_, e1_inv, nb * dw};
       dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
     }
-    HHE_DISPATCH_LOG(P_.logn - 1, {
-      constexpr int S = 1 << LOGV;
-      KsDigitsBody<LOGV> body{g1, dw, k1, acc, dC_, twref(), static_cast<int>(nb), c1n, dw, perm};
-      dev_.launch(body, nb * K * 2, ntt_threads(LOGV), (ntt_smem_words(S) + 2 * S) * 8);
-    });
+    launch_ks_digits(g1, dw, k1, acc, nb, c1n, dw, perm);
     // inverse NTT of acc[0][special] and acc[1][*]: K + 1 limbs that are contiguous inside each item
     ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, K + 1, m10, true, static_cast<size_t>(2) * K * N);
     {

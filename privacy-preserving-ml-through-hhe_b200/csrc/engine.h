@@ -97,7 +97,10 @@ class Engine {
   int batch_ = 0;
   int f64_gmin_ = 1;
   bool split_ = false;         // N = 32768 code path (split transforms)
-  bool compact_keys_ = false;  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)
+  bool compact_keys_ = false;
+  bool tmem_ks_ = false;  // FP64 key switch with accumulators in tensor memory (keys stored group-major)
+  void launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, u64 *acc, size_t items, const u64 *reuse, size_t reuse_stride,
+                        const u32 *perm);  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)
   DevConsts *dC_ = nullptr;
   W2 *dTw_ = nullptr;
   u32 *dIndex_ = nullptr;

@@ -4,18 +4,20 @@
 #pragma once
 #include "devconsts.h"
 #include "ntt_core.h"
+#include "tmem.h"
 
 namespace hhe {
 
 // global-memory IO functors for the fused first / last register pass of the FP64 transforms (ntt_core.h: SmemIO)
 struct LoadU64 {  // canonical residues -> doubles
-  static constexpr bool kLoad = true, kStore = false;
+  static constexpr bool kLoad = true, kStore = false, kGroupOut = false;
   const u64 *src;
   HD double load(int i) const { return u_to_f(src[i]); }
   HD void store(int, double) const {}
+  HD void group_out(int, const double *) const {}
 };
 struct LoadLift {  // centred lift of a plaintext coefficient into the limb (Evaluator::multiply_plain)
-  static constexpr bool kLoad = true, kStore = false;
+  static constexpr bool kLoad = true, kStore = false, kGroupOut = false;
   const u64 *src;
   u64 thr, inc;
   HD double load(int i) const {
@@ -23,18 +25,20 @@ struct LoadLift {  // centred lift of a plaintext coefficient into the limb (Eva
     return u_to_f(m >= thr ? m + inc : m);
   }
   HD void store(int, double) const {}
+  HD void group_out(int, const double *) const {}
 };
 struct StoreScaled {  // inverse transform output: multiply by N^-1, canonicalise, store
-  static constexpr bool kLoad = false, kStore = true;
+  static constexpr bool kLoad = false, kStore = true, kGroupOut = false;
   u64 *dst;
   D2 ninv;
   double q, qinv;
   HD double load(int) const { return 0.0; }
   HD void store(int i, double v) const { dst[i] = f_canonical(f_mulmod_const(v, ninv, q), q, qinv); }
+  HD void group_out(int, const double *) const {}
 };
 
 struct LoadCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[special] + half mod q_sp  (Corr0MacBody)
-  static constexpr bool kLoad = true, kStore = false;
+  static constexpr bool kLoad = true, kStore = false, kGroupOut = false;
   const u64 *sp;
   u64 half_sp, half_i, q;
   DevMod mi, msp;
@@ -44,6 +48,7 @@ struct LoadCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[spec
     return u_to_f(sub_mod(ri, half_i, q));
   }
   HD void store(int, double) const {}
+  HD void group_out(int, const double *) const {}
 };
 
 struct TwRef {
@@ -356,6 +361,199 @@ struct KsDigitsBody {
         o1[i] = barrett64(acc1[i], mk);
       }
     }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Key-switch digit kernel, tensor-memory version (FP64 path). Same computation as KsDigitsBody::run_f64, but
+//   * the 2 x N/2 inner-product accumulators of the CTA live in tensor memory (tmem.h) as a per-thread register-file
+//     extension instead of 128 KiB of shared memory  ->  68 KiB of shared memory per CTA, two CTAs per SM (512 threads each),
+//     whose phases overlap;
+//   * the multiply-accumulate with the key is fused into the last register pass of the digit transform: each thread keeps
+//     the 8 outputs of a group, multiplies them by the key and adds them to its own TMEM slots (no shared-memory round trip,
+//     one barrier less per digit). For that the key is stored "group-major": residue 8g+e of a half at e*(S/8)+g, so the
+//     key loads of a warp are contiguous (Engine::load_ksk permutes once).
+struct KsMacOut {
+  static constexpr bool kLoad = false, kStore = false, kGroupOut = true;
+  const double *k0, *k1;  // group-major key planes of (digit, component 0/1, key limb, half)
+  int G, nt;
+  double q, qi;
+  TmemAcc tm;
+  HD double load(int) const { return 0.0; }
+  HD void store(int, double) const {}
+  HD void group_out(int g, const double *x) const {
+    const int gi = g / nt;  // which of this thread's groups
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      const double *kc = (comp ? k1 : k0) + g;
+      double kv[8], a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kv[e] = kc[static_cast<size_t>(e) * G];
+      tm.ld8(gi * 2 + comp, a);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = f_add(a[e], f_mulmod_const(x[e], D2{kv[e], f_mul(kv[e], qi)}, q));
+      tm.st8(gi * 2 + comp, a);
+    }
+  }
+};
+
+template <int LOGH>
+struct KsDigitsTmemBody {
+  static constexpr const char *kName = "ks_digits";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  const u64 *target;
+  size_t stride;
+  const double *key;  // group-major FP64 key [L][2][K][N]
+  u64 *acc;           // [count][2][K][N], NTT form, canonical
+  const DevConsts *C;
+  TwRef tw;
+  int count;
+  const u64 *reuse;  // see KsDigitsBody
+  size_t reuse_stride;
+  const u32 *perm;
+  static constexpr size_t smem_bytes(int nt, bool emulate) {
+    return (ntt_smem_words(1 << LOGH) + 2) * 8 + (emulate ? static_cast<size_t>(2) * (1 << LOGH) * 8 : 0) + 0 * nt;
+  }
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH, G = S / 8;
+    const int N = 2 * S;
+    const int K = C->K, L = C->L;
+    const int b = bid / (2 * K), kh = bid % (2 * K), k = kh >> 1, h = kh & 1;
+    const int gpt = G / nt;  // groups (of 8 residues) per thread; 2 slots (components) each
+    double *fm = reinterpret_cast<double *>(smem);
+    u32 *tslot = reinterpret_cast<u32 *>(fm + ntt_smem_words(S));
+    double *emu = fm + ntt_smem_words(S) + 2;
+    (void)emu;
+    const double q = C->qf[k], qi = C->qinvf[k];
+    const F64Tw twk = tw.fwd_f(k);
+    const D2 w1{twk.idx[1], f_mul(twk.idx[1], qi)};
+    const D2 w2{twk.idx[2 + h], f_mul(twk.idx[2 + h], qi)};
+    constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
+    u32 tbase = 0;
+#if defined(__CUDA_ARCH__)
+    const int ncols = tmem_columns(nt, gpt * 2);
+    tbase = tmem_alloc_cta(tslot, ncols);
+#else
+    (void)tslot;
+#endif
+    FOR_THREADS(tid, nt) {
+      const TmemAcc tm = TmemAcc::make(tbase, tid, nt, gpt * 2, emu);
+      const double z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int s = 0; s < gpt * 2; ++s) tm.st8(s, z);
+    }
+    for (int J = 0; J < L; ++J) {
+      const double *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+      const double *k1 = k0 + static_cast<size_t>(K) * N;
+      if (reuse && J == k) {
+        // NTT_J(target_J) is the permuted NTT of the source polynomial: no transform, straight to the accumulation
+        const u64 *rn = reuse + static_cast<size_t>(b) * reuse_stride + static_cast<size_t>(J) * N;
+        const u32 *pm = perm + static_cast<size_t>(h) * S;
+        FOR_THREADS(tid, nt) {
+          const KsMacOut mac{k0, k1, G, nt, q, qi, TmemAcc::make(tbase, tid, nt, gpt * 2, emu)};
+          for (int g = tid; g < G; g += nt) {
+            u32 pj[8];
+            double x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pj[e] = pm[8 * g + e];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = u_to_f(rn[pj[e]]);
+            mac.group_out(g, x);
+          }
+        }
+        continue;
+      }
+      const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
+      if (kFold) {
+        FOR_THREADS(tid, nt) {
+          constexpr int U = 2;
+          for (int i0 = tid; i0 < S / 2; i0 += nt * U) {
+            u64 v[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * nt;
+              if (i < S / 2) {
+                v[u][0] = dig[i];
+                v[u][1] = dig[i + S];
+                v[u][2] = dig[i + S / 2];
+                v[u][3] = dig[i + S / 2 + S];
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int i = i0 + u * nt;
+              if (i < S / 2) {
+                const double t0 = f_mulmod_const(u_to_f(v[u][1]), w1, q), t1 = f_mulmod_const(u_to_f(v[u][3]), w1, q);
+                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);
+                const double a1 = h ? f_add(u_to_f(v[u][2]), -t1) : f_add(u_to_f(v[u][2]), t1);
+                const double tt = f_mulmod_const(a1, w2, q);
+                fm[pidx(i)] = f_add(a0, tt);
+                fm[pidx(i + S / 2)] = f_add(a0, -tt);
+              }
+            }
+          }
+        }
+      } else {
+        FOR_THREADS(tid, nt) {
+          for (int i = tid; i < S; i += nt) {
+            const double t = f_mulmod_const(u_to_f(dig[i + S]), w1, q);
+            fm[pidx(i)] = h ? f_add(u_to_f(dig[i]), -t) : f_add(u_to_f(dig[i]), t);
+          }
+        }
+      }
+      SYNC();
+      // register passes; the last one hands its outputs to KsMacOut::group_out. The functor is rebuilt per thread inside
+      // the chain's FOR_THREADS through TmemAcc::make, so pass the ingredients.
+      run_passes<kFold>(fm, twk, q, qi, h, nt, k0, k1, tbase, gpt, emu);
+      SYNC();  // the next digit's load overwrites fm
+    }
+    // write-out: TMEM -> canonical residues -> global (through shared memory so that stores are coalesced)
+    u64 *fo = reinterpret_cast<u64 *>(fm);
+    for (int comp = 0; comp < 2; ++comp) {
+      FOR_THREADS(tid, nt) {
+        const TmemAcc tm = TmemAcc::make(tbase, tid, nt, gpt * 2, emu);
+        for (int g = tid; g < G; g += nt) {
+          double a[8];
+          tm.ld8((g / nt) * 2 + comp, a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) fo[pidx(8 * g + e)] = f_canonical(a[e], q, qi);
+        }
+      }
+      SYNC();
+      u64 *o = acc + ((static_cast<size_t>(b) * 2 + comp) * K + k) * N + static_cast<size_t>(h) * S;
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) o[i] = fo[pidx(i)];
+      }
+      SYNC();
+    }
+#if defined(__CUDA_ARCH__)
+    tmem_free_cta(tbase, ncols);
+#endif
+  }
+
+  // IO functor that rebuilds the per-thread TMEM view from the thread index of the group it is called for
+  struct MacIO {
+    static constexpr bool kLoad = false, kStore = false, kGroupOut = true;
+    const double *k0, *k1;
+    int G, nt, slots;
+    double q, qi;
+    u32 tbase;
+    double *emu;
+    HD double load(int) const { return 0.0; }
+    HD void store(int, double) const {}
+    HD void group_out(int g, const double *x) const {
+      const KsMacOut mac{k0, k1, G, nt, q, qi, TmemAcc::make(tbase, g % nt, nt, slots, emu)};
+      mac.group_out(g, x);
+    }
+  };
+  template <bool FOLD>
+  HD void run_passes(double *fm, F64Tw twk, double q, double qi, int h, int nt, const double *k0, const double *k1, u32 tbase, int gpt,
+                     double *emu) const {
+    constexpr int G = (1 << LOGH) / 8;
+    const MacIO io{k0, k1, G, nt, gpt * 2, q, qi, tbase, emu};
+    if (FOLD)
+      ntt_fwd_core_f64_from<LOGH, 1, (FOLD ? 1 : 0), 8>(fm, twk, q, qi, h, nt, io);
+    else
+      ntt_fwd_core_f64<LOGH, 1, 6>(fm, twk, q, qi, h, nt, io);
   }
 };
 
@@ -1083,6 +1281,7 @@ struct ShoupifyBody {
   const DevConsts *C;
   size_t total;
   int compact_f64;
+  int group_major;  // FP64 compact keys for KsDigitsTmemBody: residue 8g+e of each half limb goes to e*(N/16)+g
   HD void operator()(int bid, int nt, unsigned char *) const {
     const size_t N = C->N;
     FOR_THREADS(tid, nt) {
@@ -1092,7 +1291,12 @@ struct ShoupifyBody {
         const DevMod m = C->mod[limb];
         const u64 w = in[g];
         if (compact_f64) {
-          reinterpret_cast<double *>(out)[g] = u_to_f(w);
+          size_t dst = g;
+          if (group_major) {
+            const size_t half = N >> 1, p = g & (N - 1), r = p & (half - 1);
+            dst = (g - p) + (p - r) + (r & 7) * (half >> 3) + (r >> 3);
+          }
+          reinterpret_cast<double *>(out)[dst] = u_to_f(w);
         } else {
         // floor(w * 2^64 / q): Barrett estimate from floor(2^128/q), then exact correction
         u64 est = mulhi64(w, m.cr0) + w * m.cr1;

@@ -26,8 +26,18 @@ inline void cuda_check(cudaError_t e, const char *what) {
   if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+// launch bounds: bodies may declare kMaxThreads / kMinBlocks (e.g. 512 x 2 CTAs per SM); default HHE_MAX_THREADS x 1
+template <class B, class = void>
+struct BodyBounds {
+  static constexpr int kT = HHE_MAX_THREADS, kM = 1;
+};
+template <class B>
+struct BodyBounds<B, decltype(void(B::kMinBlocks))> {
+  static constexpr int kT = B::kMaxThreads, kM = B::kMinBlocks;
+};
+
 template <class Body>
-__global__ void __launch_bounds__(HHE_MAX_THREADS) kernel_entry(const Body body) {
+__global__ void __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry(const Body body) {
   extern __shared__ __align__(16) unsigned char hhe_smem[];
   body(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
 }

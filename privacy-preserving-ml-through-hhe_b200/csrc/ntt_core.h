@@ -191,10 +191,13 @@ HD size_t f64tw_offset(int g0, int gmin) {
 // IO::load(i) and the inverse transform's last pass (S0 == 0) can hand its outputs to IO::store(i, v) instead of going
 // through shared memory: in both, consecutive threads touch consecutive residues (coalesced), and one shared-memory
 // round trip plus one barrier per transform disappear.
+// A third hook, IO::group_out(g, x), receives the 8 outputs of every group of the forward transform's LAST pass in
+// registers (the key-switch kernel multiplies them by the key and accumulates without another shared-memory round trip).
 struct SmemIO {
-  static constexpr bool kLoad = false, kStore = false;
+  static constexpr bool kLoad = false, kStore = false, kGroupOut = false;
   HD double load(int) const { return 0.0; }
   HD void store(int, double) const {}
+  HD void group_out(int, const double *) const {}
 };
 
 template <int R, bool INVERSE, int LOGS, int S0, int LM, class IO = SmemIO>
@@ -221,6 +224,7 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   }
   constexpr bool kGlobalIn = IO::kLoad && !INVERSE && S0 == 0;
   constexpr bool kGlobalOut = IO::kStore && INVERSE && S0 == 0;
+  constexpr bool kGroupOut = IO::kGroupOut && !INVERSE && S0 + R == LOGS;
   double x[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) x[e] = kGlobalIn ? io.load((hi << (LOGS - S0)) + lo + (e << LG)) : sm[a0 + off(e)];
@@ -261,6 +265,10 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
       }
     }
   }
+  if (kGroupOut) {
+    io.group_out(g, x);
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     if (kGlobalOut)
@@ -284,7 +292,7 @@ struct FwdChainF64 {
       for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, false, LOGS, S0, LM, IO>(sm, tw, q, qinv, chunk, g, kReduce, io);
     }
     SYNC();
-    if (S0 + R < LOGS) FwdChainF64<LOGS, LM, (S0 + R < LOGS ? S0 + R : 0), (S0 + R < LOGS ? kOut : 0)>::run(sm, tw, q, qinv, chunk, nt);
+    if (S0 + R < LOGS) FwdChainF64<LOGS, LM, (S0 + R < LOGS ? S0 + R : 0), (S0 + R < LOGS ? kOut : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
@@ -296,9 +304,9 @@ HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk,
 }
 
 // Same, entering the chain at local stage S0 (the caller already performed the stages below S0).
-template <int LOGS, int LM, int S0, int B2IN>
-HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt) {
-  FwdChainF64<LOGS, LM, S0, B2IN>::run(sm, tw, q, qinv, chunk, nt);
+template <int LOGS, int LM, int S0, int B2IN, class IO = SmemIO>
+HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
+  FwdChainF64<LOGS, LM, S0, B2IN>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 // Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2: differences stay <= 4q).
