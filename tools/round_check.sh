@@ -10,5 +10,5 @@ $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 3000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:KsDigits -s 30 -c 1 -o gpurun_out/prof_ksdigits $CMD > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:KsDigitsTmem -s 30 -c 1 -o gpurun_out/prof_ksdigits $CMD > gpurun_out/ncu2.log 2>&1
 echo "full capture rc=$?"
