@@ -581,11 +581,14 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb) {
   dev_.d2d(rot, state, nb * ctw * 8);
   for (int j = 1; j < N1; ++j) rotate_rows(rot + (j - 1) * nb * ctw, -1, 0, rot + j * nb * ctw, nb);
   const TabMap mq = map_mod(2 * P_.L, P_.L, 0);
+  // every baby rotation is multiplied with 8 diagonals: transform each once (in place), then the products are element-wise
+  ntt(rot, rot, nb * N1, 2 * P_.L, mq, false);
   for (int k = 0; k < N2; ++k) {
     for (int j = 0; j < N1; ++j) {
       encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt, nb);
       lift_ntt(pt, D, nb);
-      ntt_mac(rot + j * nb * ctw, D, dw, inner, nb, j == 0);
+      DyadicMacBody mac{rot + j * nb * ctw, D, inner, dC_, j == 0 ? 1 : 0, nb * ctw};
+      dev_.launch(mac, ew_grid(nb * ctw), kEwThreads, 0);
     }
     if (k == 0) {
       ntt(inner, outer, nb, 2 * P_.L, mq, true);

@@ -1051,6 +1051,35 @@ struct NttMacBody {
 };
 
 // ------------------------------------------------------------------------------------------------------------
+// Element-wise plaintext product in the NTT domain: sum[b][c][i] (+)= a[b][c][i] (.) D[b][i]  (a already transformed).
+// The baby-step/giant-step affine layer transforms each of its 16 baby rotations once and reuses them for all 8
+// giant steps (pasta_3_seal.cpp:349-365 multiplies every rot[j] with 8 different diagonals).
+struct DyadicMacBody {
+  static constexpr const char *kName = "dyadic_mac";
+  const u64 *a;  // [items][2][L][N] NTT form
+  const u64 *D;  // [items][L][N]
+  u64 *sum;      // [items][2][L][N]
+  const DevConsts *C;
+  int first;
+  size_t total;  // items * 2 * L * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    const u32 L = static_cast<u32>(C->L);
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const u32 limb = static_cast<u32>(g >> C->logn);
+        const u32 i = limb % L, item = limb / (2 * L);
+        const DevMod mi = C->mod[i];
+        u64 v = mul_mod(a[g], D[(static_cast<size_t>(item) * L + i) * N + (g & (N - 1))], mi);
+        if (!first) v = add_mod(v, sum[g], mi.q);
+        sum[g] = v;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
 // BEHZ multiplication (Evaluator::bfv_multiply, seal/evaluator.h:214; RNSTool, seal/util/rns.h:213-228)
 
 // fastbconv_m_tilde + sm_mrq: x (base q, coefficient form) -> x in base Bsk.  One thread per (poly, coefficient).
