@@ -23,6 +23,7 @@ struct DevConsts {
   u64 half_sp;
   u64 half_sp_mod_q[kMaxLimbs];
   W2 inv_sp_mod_q[kMaxLimbs];
+  D2 inv_sp_f[kMaxLimbs];  // the same constant for the FP64 path
   // BEHZ
   W2 mtilde_ipq[kMaxLimbs];  // m_tilde * (Q/q_i)^-1 mod q_i
   W2 t_ipq[kMaxLimbs];       // t * (Q/q_i)^-1 mod q_i
@@ -93,6 +94,8 @@ inline DevConsts make_devconsts(const Params &p) {
     c.q_div_t_mod_q[i] = p.q_div_t_mod_q[i];
     c.half_sp_mod_q[i] = p.half_sp_mod_q[i];
     c.inv_sp_mod_q[i] = w2(p.inv_sp_mod_q[i]);
+    if (i < p.L && p.q[i])
+      c.inv_sp_f[i] = D2{static_cast<double>(p.inv_sp_mod_q[i].w), static_cast<double>(p.inv_sp_mod_q[i].w) / static_cast<double>(p.q[i])};
     c.mtilde_ipq[i] = w2(p.mtilde_mod_q[i]);
     c.t_ipq[i] = w2(p.t_inv_punct_q[i]);
     c.q2mt[i] = p.q2mt[i];

@@ -88,6 +88,7 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   compact_keys_ = true;
   for (int k = 0; k < P_.K; ++k) compact_keys_ = compact_keys_ && table_is_f64(P_, k);
   tmem_ks_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_TMEM");
+  half_fwd_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_HALF");
   std::vector<W2> tw(ntab * 2 * P_.N);
   for (size_t t = 0; t < ntab; ++t) {
     if (!P_.tab[t].q) continue;
@@ -199,8 +200,10 @@ const W2 *Engine::need_key(int kind, u32 elt) const {
 }
 
 // ------------------------------------------------------------------------------------------------ primitives
-void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride) {
+void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride,
+                 size_t limb_stride) {
   if (split_) {
+    if (limb_stride) throw std::invalid_argument("strided limbs are not supported by the split transforms");
     const size_t stride = item_stride ? item_stride : static_cast<size_t>(limbs) * P_.N;
     Scope sc(*this);
     if (!inverse && in == out) {
@@ -222,7 +225,8 @@ void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap 
     return;
   }
   HHE_DISPATCH_LOG(P_.logn, {
-    NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, item_stride ? item_stride : static_cast<size_t>(limbs) << LOGV};
+    NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, item_stride ? item_stride : static_cast<size_t>(limbs) << LOGV,
+                        limb_stride ? limb_stride : static_cast<size_t>(1) << LOGV};
     dev_.launch(body, items * limbs, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
 }
@@ -273,6 +277,13 @@ void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode
 
 void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
   require_whole_limb("multiply_plain");
+  if (half_fwd_) {
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      LiftNttHalfBody<LOGV> body{pt, D, dC_, twref()};
+      dev_.launch(body, items * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    return;
+  }
   HHE_DISPATCH_LOG(P_.logn, {
     LiftNttBody<LOGV> body{pt, D, dC_, twref()};
     dev_.launch(body, items * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -282,6 +293,13 @@ void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
 void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps, size_t sum_off,
                      u64 *ntt_out) {
   require_whole_limb("multiply_plain");
+  if (half_fwd_) {
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      NttMacHalfBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out};
+      dev_.launch(body, items * comps * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    return;
+  }
   HHE_DISPATCH_LOG(P_.logn, {
     NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out};
     dev_.launch(body, items * comps * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -539,28 +557,36 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   strided_copy(stn, ctw, c0a, dw, dw, nb);
   strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
   strided_copy(state + dw, ctw, c1c, dw, dw, nb);
-  TabMap m10{};
-  m10.id[0] = static_cast<unsigned char>(K - 1);
-  for (int k = 0; k < K; ++k) m10.id[1 + k] = static_cast<unsigned char>(k);
   u64 *c0_in = c0a, *c0_out = c0b;
+  TabMap msp2{};
+  msp2.id[0] = msp2.id[1] = static_cast<unsigned char>(K - 1);
+  {  // g1 = galois(c1) in coefficient form: the digits of the first key switch (later ones come out of intt_moddown)
+    GaloisBody gb{c1c, g1, dC_, e1_inv, nb * dw};
+    dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
+  }
   for (int i = 1; i < kPastaT; ++i) {
-    {  // g1 = galois(c1) in coefficient form: the digits of the key switch
-      GaloisBody gb{c1c, g1, dC_, e1_inv, nb * dw};
-      dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
-    }
     launch_ks_digits(g1, dw, k1, acc, nb, c1n, dw, perm);
-    // inverse NTT of acc[0][special] and acc[1][*]: K + 1 limbs that are contiguous inside each item
-    ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, K + 1, m10, true, static_cast<size_t>(2) * K * N);
-    {
-      ModDownC1Body md{acc, c1c, dC_, nb * N};
-      dev_.launch(md, ew_grid(nb * N), kEwThreads, 0);
-    }
-    encode_material(mat, nullptr, kDiag, layer, i, pt, nb);
-    lift_ntt(pt, D, nb);
+    // inverse NTT of the two special limbs acc[0][K-1], acc[1][K-1] (K*N words apart inside an item), then of acc[1][i<L]
+    // with the ModDown and the next rotation's Galois map fused into the store
+    ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, 2, msp2, true, static_cast<size_t>(2) * K * N,
+        static_cast<size_t>(K) * N);
     HHE_DISPATCH_LOG(P_.logn, {
-      Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref()};
+      InttModDownBody<LOGV> body{acc, c1c, g1, dC_, twref(), e1};
       dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
     });
+    encode_material(mat, nullptr, kDiag, layer, i, pt, nb);
+    lift_ntt(pt, D, nb);
+    if (half_fwd_) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref()};
+        dev_.launch(body, nb * L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+    } else {
+      HHE_DISPATCH_LOG(P_.logn, {
+        Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref()};
+        dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+    }
     std::swap(c0_in, c0_out);
     ntt_mac(c1c, D, dw, sum, nb, false, 1, dw, c1n);
   }

@@ -41,7 +41,8 @@ class Engine {
   const W2 *find_key(int kind, u32 elt) const;
 
   // ---- primitives (device pointers) ----
-  void ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride = 0);
+  void ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride = 0,
+           size_t limb_stride = 0);
   void add(const u64 *a, const u64 *b, u64 *out, size_t items, int size = 2);
   void negate(const u64 *a, u64 *out, size_t items);
   void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first);
@@ -99,6 +100,7 @@ class Engine {
   bool split_ = false;         // N = 32768 code path (split transforms)
   bool compact_keys_ = false;
   bool tmem_ks_ = false;  // FP64 key switch with accumulators in tensor memory (keys stored group-major)
+  bool half_fwd_ = false;  // FP64 forward transforms of lift_ntt / ntt_mac / corr0_mac as half-limb CTAs (two per SM)
   void launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, u64 *acc, size_t items, const u64 *reuse, size_t reuse_stride,
                         const u32 *perm);  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)
   DevConsts *dC_ = nullptr;

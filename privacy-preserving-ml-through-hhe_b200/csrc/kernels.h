@@ -68,6 +68,114 @@ struct TwRef {
   }
 };
 
+// Key-switch digit transforms (FP64 path): digits are residues mod q_J <= 2 q_k. Bounds in units of q_k / 2 after one /
+// two folded Cooley-Tukey stages (2 + 0.94 and 2.94 + 1.13), and the bound (units of q_k / 16) the inner product accepts
+// from the transform: 8 products of magnitude <= 1.25 q_k keep the accumulators below 10 q_k.
+constexpr int kKsFold1 = 6, kKsFold2 = 9, kKsOut16 = 64;
+
+// ------------------------------------------------------------------------------------------------------------
+// Half-limb forward transforms (FP64 path). The first Cooley-Tukey stage of an N-point transform pairs residue i with
+// i + N/2; after it the two halves are independent N/2-point transforms. A CTA that owns half h applies that stage while
+// loading (it reads the whole limb, L2 serves the second reader) and then needs only N/2 doubles of shared memory
+// (68 KiB at N = 16384): two CTAs per SM, whose load, barrier and store phases overlap. When the sub-transform's
+// odd-sized first register pass is a single stage it is folded into the load too.
+// LD: raw(i) fetches input residue i of the limb (global memory), cvt() turns it into a double of magnitude <= 2q.
+struct RawU64 {
+  const u64 *src;
+  HD u64 raw(int i) const { return src[i]; }
+  HD double cvt(u64 v) const { return u_to_f(v); }
+};
+struct RawLift {  // centred lift of a plaintext coefficient into the limb (Evaluator::multiply_plain)
+  const u64 *src;
+  u64 thr, inc;
+  HD u64 raw(int i) const { return src[i]; }
+  HD double cvt(u64 m) const { return u_to_f(m >= thr ? m + inc : m); }
+};
+struct RawCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[special] + half mod q_sp  (Corr0Mac)
+  const u64 *sp;
+  u64 half_sp, half_i, q;
+  DevMod mi, msp;
+  HD u64 raw(int j) const { return sp[j]; }
+  HD double cvt(u64 v) const {
+    const u64 r = csub(v + half_sp, msp.q);
+    const u64 ri = msp.q > q ? barrett64(r, mi) : r;
+    return u_to_f(sub_mod(ri, half_i, q));
+  }
+};
+
+template <int LOGH, class LD>
+HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const LD &ld) {
+  constexpr int S = 1 << LOGH;
+  constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
+  const D2 w1{twk.idx[1], f_mul(twk.idx[1], qi)};
+  if (kFold) {
+    const D2 w2{twk.idx[2 + h], f_mul(twk.idx[2 + h], qi)};
+    FOR_THREADS(tid, nt) {
+      // software pipeline: the four loads of iteration n+1 are in flight while iteration n is computed
+      u64 v[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0};
+      if (tid < S / 2) {
+        v[0] = ld.raw(tid);
+        v[1] = ld.raw(tid + S);
+        v[2] = ld.raw(tid + S / 2);
+        v[3] = ld.raw(tid + S / 2 + S);
+      }
+      for (int i = tid; i < S / 2; i += nt) {
+        const int in = i + nt;
+        if (in < S / 2) {
+          nv[0] = ld.raw(in);
+          nv[1] = ld.raw(in + S);
+          nv[2] = ld.raw(in + S / 2);
+          nv[3] = ld.raw(in + S / 2 + S);
+        }
+        const double t0 = f_mulmod_const(ld.cvt(v[1]), w1, q), t1 = f_mulmod_const(ld.cvt(v[3]), w1, q);
+        const double a0 = h ? f_add(ld.cvt(v[0]), -t0) : f_add(ld.cvt(v[0]), t0);  // |.| <= 2.94q
+        const double a1 = h ? f_add(ld.cvt(v[2]), -t1) : f_add(ld.cvt(v[2]), t1);
+        const double tt = f_mulmod_const(a1, w2, q);
+        fm[pidx(i)] = f_add(a0, tt);  // |.| <= 4.1q
+        fm[pidx(i + S / 2)] = f_add(a0, -tt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = nv[e];
+      }
+    }
+  } else {
+    FOR_THREADS(tid, nt) {
+      constexpr int U = 4;
+      for (int i0 = tid; i0 < S; i0 += nt * U) {
+        u64 xs[U], ys[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * nt;
+          if (i < S) {
+            xs[u] = ld.raw(i);
+            ys[u] = ld.raw(i + S);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * nt;
+          if (i < S) {
+            const double t = f_mulmod_const(ld.cvt(ys[u]), w1, q);
+            fm[pidx(i)] = h ? f_add(ld.cvt(xs[u]), -t) : f_add(ld.cvt(xs[u]), t);  // |.| <= 2.94q
+          }
+        }
+      }
+    }
+  }
+  SYNC();
+}
+
+// the register passes that follow fwd_half_load_f64; results in shared memory (or handed to IO::group_out), |.| <= MAXOUT16/16 q
+template <int LOGH, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16>
+HD void fwd_half_passes_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const IO &io = IO()) {
+  constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
+  if (kFold)
+    ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), kKsFold2, IO, MAXOUT16>(fm, twk, q, qi, h, nt, io);
+  else
+    ntt_fwd_core_f64<LOGH, 1, kKsFold1, IO, MAXOUT16>(fm, twk, q, qi, h, nt, io);
+}
+
+constexpr int half_threads(int logh) { return (1 << logh) / 8 < 32 ? 32 : ((1 << logh) / 8 > 512 ? 512 : (1 << logh) / 8); }
+
 constexpr int kMaxMapLimbs = 3 * kMaxLimbs;  // size-3 ciphertext in the Bsk base
 struct TabMap {  // limb index inside an item -> NTT table id
   unsigned char id[kMaxMapLimbs];
@@ -87,12 +195,13 @@ struct NttBody {
   int limbs;
   int inverse;
   size_t istride;  // words between consecutive items (limbs * N when dense)
+  size_t lstride;  // words between consecutive limbs of an item (N when dense)
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     u64 *sm = reinterpret_cast<u64 *>(smem);
     const int tab = map.id[bid % limbs];
     const u64 q = C->mod[tab].q;
-    const size_t at = static_cast<size_t>(bid / limbs) * istride + static_cast<size_t>(bid % limbs) * S;
+    const size_t at = static_cast<size_t>(bid / limbs) * istride + static_cast<size_t>(bid % limbs) * lstride;
     const u64 *src = in + at;
     u64 *dst = out + at;
     if (C->f64[tab]) {  // FP64-pipe transform (modarith_f64.h)
@@ -215,17 +324,17 @@ struct KsDigitsBody {
               const int i = i0 + u * nt;
               if (i < S / 2) {
                 const double t0 = f_mulmod_const(u_to_f(v[u][1]), w1, q), t1 = f_mulmod_const(u_to_f(v[u][3]), w1, q);
-                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);  // |.| <= 3q
+                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);  // |.| <= 2.94q
                 const double a1 = h ? f_add(u_to_f(v[u][2]), -t1) : f_add(u_to_f(v[u][2]), t1);
                 const double tt = f_mulmod_const(a1, w2, q);
-                fm[pidx(i)] = f_add(a0, tt);  // |.| <= 4q
+                fm[pidx(i)] = f_add(a0, tt);  // |.| <= 4.1q
                 fm[pidx(i + S / 2)] = f_add(a0, -tt);
               }
             }
           }
         }
         SYNC();
-        ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), 8>(fm, twk, q, qi, h, nt);
+        ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), kKsFold2, SmemIO, kKsOut16>(fm, twk, q, qi, h, nt);
       } else {
         FOR_THREADS(tid, nt) {
           constexpr int U = 4;
@@ -242,13 +351,13 @@ struct KsDigitsBody {
               const int i = i0 + u * nt;
               if (i < S) {
                 const double t = f_mulmod_const(u_to_f(ys[u]), w1, q);
-                fm[pidx(i)] = h ? f_add(u_to_f(xs[u]), -t) : f_add(u_to_f(xs[u]), t);  // |.| <= 3q
+                fm[pidx(i)] = h ? f_add(u_to_f(xs[u]), -t) : f_add(u_to_f(xs[u]), t);  // |.| <= 2.94q
               }
             }
           }
         }
         SYNC();
-        ntt_fwd_core_f64<LOGH, 1, 6>(fm, twk, q, qi, h, nt);
+        ntt_fwd_core_f64<LOGH, 1, kKsFold1, SmemIO, kKsOut16>(fm, twk, q, qi, h, nt);
       }
       // compact FP64 key: double[L][2][K][N] (8 bytes per residue; k/q is formed as k * (1/q))
       const double *k0 = reinterpret_cast<const double *>(key) + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
@@ -258,9 +367,9 @@ struct KsDigitsBody {
         for (int i = tid; i < S; i += nt) {
           const double v = fm[pidx(i)];
           const double a = k0[i], c = k1[i];
-          // L <= 8 terms of magnitude <= q: |acc| <= 8q <= 2^52, every partial sum is an exact integer
-          acc0[i] = f_add(acc0[i], f_mulmod_const(v, D2{a, f_mul(a, qi)}, q));
-          acc1[i] = f_add(acc1[i], f_mulmod_const(v, D2{c, f_mul(c, qi)}, q));
+          // L <= 8 terms of magnitude <= 1.25q (|v| <= 4q, kKsOut16): |acc| <= 10q < 2^53, every partial sum is an exact integer
+          acc0[i] = f_add(acc0[i], f_mulmod_var(v, a, q, qi));
+          acc1[i] = f_add(acc1[i], f_mulmod_var(v, c, q, qi));
         }
       }
       SYNC();
@@ -391,7 +500,7 @@ struct KsMacOut {
       for (int e = 0; e < 8; ++e) kv[e] = kc[static_cast<size_t>(e) * G];
       tm.ld8(gi * 2 + comp, a);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = f_add(a[e], f_mulmod_const(x[e], D2{kv[e], f_mul(kv[e], qi)}, q));
+      for (int e = 0; e < 8; ++e) a[e] = f_add(a[e], f_mulmod_var(x[e], kv[e], q, qi));
       tm.st8(gi * 2 + comp, a);
     }
   }
@@ -426,8 +535,6 @@ struct KsDigitsTmemBody {
     (void)emu;
     const double q = C->qf[k], qi = C->qinvf[k];
     const F64Tw twk = tw.fwd_f(k);
-    const D2 w1{twk.idx[1], f_mul(twk.idx[1], qi)};
-    const D2 w2{twk.idx[2 + h], f_mul(twk.idx[2 + h], qi)};
     constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
     u32 tbase = 0;
 #if defined(__CUDA_ARCH__)
@@ -463,44 +570,7 @@ struct KsDigitsTmemBody {
         continue;
       }
       const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
-      if (kFold) {
-        FOR_THREADS(tid, nt) {
-          constexpr int U = 2;
-          for (int i0 = tid; i0 < S / 2; i0 += nt * U) {
-            u64 v[U][4];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int i = i0 + u * nt;
-              if (i < S / 2) {
-                v[u][0] = dig[i];
-                v[u][1] = dig[i + S];
-                v[u][2] = dig[i + S / 2];
-                v[u][3] = dig[i + S / 2 + S];
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int i = i0 + u * nt;
-              if (i < S / 2) {
-                const double t0 = f_mulmod_const(u_to_f(v[u][1]), w1, q), t1 = f_mulmod_const(u_to_f(v[u][3]), w1, q);
-                const double a0 = h ? f_add(u_to_f(v[u][0]), -t0) : f_add(u_to_f(v[u][0]), t0);
-                const double a1 = h ? f_add(u_to_f(v[u][2]), -t1) : f_add(u_to_f(v[u][2]), t1);
-                const double tt = f_mulmod_const(a1, w2, q);
-                fm[pidx(i)] = f_add(a0, tt);
-                fm[pidx(i + S / 2)] = f_add(a0, -tt);
-              }
-            }
-          }
-        }
-      } else {
-        FOR_THREADS(tid, nt) {
-          for (int i = tid; i < S; i += nt) {
-            const double t = f_mulmod_const(u_to_f(dig[i + S]), w1, q);
-            fm[pidx(i)] = h ? f_add(u_to_f(dig[i]), -t) : f_add(u_to_f(dig[i]), t);
-          }
-        }
-      }
-      SYNC();
+      fwd_half_load_f64<LOGH>(fm, twk, q, qi, h, nt, RawU64{dig});  // ends with a barrier
       // register passes; the last one hands its outputs to KsMacOut::group_out. The functor is rebuilt per thread inside
       // the chain's FOR_THREADS through TmemAcc::make, so pass the ingredients.
       run_passes<kFold>(fm, twk, q, qi, h, nt, k0, k1, tbase, gpt, emu);
@@ -551,9 +621,9 @@ struct KsDigitsTmemBody {
     constexpr int G = (1 << LOGH) / 8;
     const MacIO io{k0, k1, G, nt, gpt * 2, q, qi, tbase, emu};
     if (FOLD)
-      ntt_fwd_core_f64_from<LOGH, 1, (FOLD ? 1 : 0), 8>(fm, twk, q, qi, h, nt, io);
+      ntt_fwd_core_f64_from<LOGH, 1, (FOLD ? 1 : 0), kKsFold2, MacIO, kKsOut16>(fm, twk, q, qi, h, nt, io);
     else
-      ntt_fwd_core_f64<LOGH, 1, 6>(fm, twk, q, qi, h, nt, io);
+      ntt_fwd_core_f64<LOGH, 1, kKsFold1, MacIO, kKsOut16>(fm, twk, q, qi, h, nt, io);
   }
 };
 
@@ -1299,6 +1369,207 @@ struct Corr0MacBody {
         }
       }
     }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Half-limb versions (FP64 path, two CTAs per SM) of lift_ntt / ntt_mac / corr0_mac: CTA = (limb, half).
+template <int LOGH>
+struct LiftNttHalfBody {
+  static constexpr const char *kName = "lift_ntt";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  const u64 *pt;  // [items][N]
+  u64 *out;       // [items][L][N]
+  const DevConsts *C;
+  TwRef tw;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH;
+    const int h = bid & 1, lb = bid >> 1;
+    const int L = C->L, i = lb % L;
+    const size_t item = lb / L;
+    const u64 q = C->mod[i].q;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[i], qi = C->qinvf[i];
+    const F64Tw twk = tw.fwd_f(i);
+    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawLift{pt + item * (2 * S), C->half_t, q - C->t});
+    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
+    u64 *dst = out + static_cast<size_t>(lb) * (2 * S) + static_cast<size_t>(h) * S;
+    FOR_THREADS(tid, nt) {
+#pragma unroll 4
+      for (int j = tid; j < S; j += nt) dst[j] = f_canonical(fm[pidx(j)], qd, qi);
+    }
+  }
+};
+
+template <int LOGH>
+struct NttMacHalfBody {
+  static constexpr const char *kName = "ntt_mac";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  const u64 *ct;  // [items][comps][L][N] coefficient form
+  const u64 *D;   // [items][L][N] (dstride = L*N) or shared (dstride = 0)
+  size_t dstride;
+  u64 *sum;
+  const DevConsts *C;
+  TwRef tw;
+  int first;  // 1: overwrite
+  int comps;
+  size_t sum_stride, sum_off;
+  u64 *ntt_out;  // optional: NTT_i(ct) itself (canonical), same indexing as ct
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH;
+    const int h = bid & 1, lb = bid >> 1;
+    const int L = C->L, i = lb % L;
+    const size_t item = lb / (comps * L);
+    const int cl = lb % (comps * L);
+    const size_t hoff = static_cast<size_t>(h) * S;
+    const u64 *d = D + item * dstride + static_cast<size_t>(i) * (2 * S) + hoff;
+    u64 *dst = sum + item * sum_stride + sum_off + static_cast<size_t>(cl) * (2 * S) + hoff;
+    u64 *nout = ntt_out ? ntt_out + static_cast<size_t>(lb) * (2 * S) + hoff : nullptr;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[i], qi = C->qinvf[i];
+    const F64Tw twk = tw.fwd_f(i);
+    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawU64{ct + static_cast<size_t>(lb) * (2 * S)});
+    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
+    FOR_THREADS(tid, nt) {
+      constexpr int U = 4;
+      for (int j0 = tid; j0 < S; j0 += nt * U) {
+        u64 dv[U], sv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt < S ? j0 + u * nt : j0;
+          dv[u] = d[j];
+          sv[u] = first ? 0 : dst[j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt;
+          if (j < S) {
+            const double x = fm[pidx(j)];
+            if (nout) nout[j] = f_canonical(x, qd, qi);
+            // |x| <= 10q: the product is bounded by 2.4q, plus the canonical running sum
+            dst[j] = f_canonical(f_add(f_mulmod_var(x, u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
+          }
+        }
+      }
+    }
+  }
+};
+
+template <int LOGH>
+struct Corr0MacHalfBody {
+  static constexpr const char *kName = "corr0_mac";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  const u64 *acc;     // [items][2][K][N]: [0][K-1] coefficient form (after the inverse NTT), [0][i<L] NTT form
+  const u64 *c0_in;   // [items][L][N] NTT form
+  u64 *c0_out;        // [items][L][N]
+  const u32 *perm;    // NTT-slot permutation of the Galois element
+  const u64 *D;       // [items][L][N]
+  u64 *sum;           // [items][2][L][N], component 0 updated
+  const DevConsts *C;
+  TwRef tw;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH;
+    const int h = bid & 1, lb = bid >> 1;
+    const int L = C->L, K = C->K, i = lb % L;
+    const size_t item = lb / L, N = 2 * S, hoff = static_cast<size_t>(h) * S;
+    const DevMod mi = C->mod[i], msp = C->mod[K - 1];
+    const u64 *sp = acc + ((item * 2) * K + (K - 1)) * N;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[i], qi = C->qinvf[i];
+    const F64Tw twk = tw.fwd_f(i);
+    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
+    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
+    const u64 *a0 = acc + ((item * 2) * K + i) * N + hoff;
+    const u64 *cin = c0_in + (item * L + i) * N;
+    u64 *cout = c0_out + (item * L + i) * N + hoff;
+    const u64 *d = D + (item * L + i) * N + hoff;
+    u64 *s0 = sum + (item * 2 * L + i) * N + hoff;
+    const u32 *pm = perm + hoff;
+    const D2 isp = C->inv_sp_f[i];
+    FOR_THREADS(tid, nt) {
+      constexpr int U = 4;  // independent gathers in flight per thread (perm -> c0 is a dependent pair of loads)
+      for (int j0 = tid; j0 < S; j0 += nt * U) {
+        u32 pj[U];
+        u64 cv[U], av[U], dv[U], sv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pj[u] = pm[j0 + u * nt < S ? j0 + u * nt : j0];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt < S ? j0 + u * nt : j0;
+          cv[u] = cin[pj[u]];
+          av[u] = a0[j];
+          dv[u] = d[j];
+          sv[u] = s0[j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt;
+          if (j < S) {
+            // k0 = (acc0 - NTT(corr)) * q_sp^-1: |acc0 - NTT(corr)| <= 11q, |k0| <= 2.6q
+            const double k0 = f_mulmod_const(f_add(u_to_f(av[u]), -fm[pidx(j)]), isp, qd);
+            const u64 c = f_canonical(f_add(u_to_f(cv[u]), k0), qd, qi);
+            cout[j] = c;
+            s0[j] = f_canonical(f_add(f_mulmod_var(u_to_f(c), u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
+          }
+        }
+      }
+    }
+  }
+};
+
+// Inverse NTT of the component-1 accumulator limbs of a key switch with the rounding ModDown and the Galois map of the
+// NEXT rotation fused into the store (NTT-resident rotation chain, FP64 path). CTA per (item, limb i < L):
+//   c1[i][j]       = (INTT(acc1[i])[j] - ((r1[j] + half) mod q_sp) + half_i) * q_sp^-1  mod q_i     (switch_key_inplace)
+//   g1[i][pi(j)]   = +- c1[i][j]   with pi(j) = j * elt mod N, sign from bit log N of j * elt        (apply_galois)
+// r1 = acc1[special] must already be in coefficient form (a two-limb launch of NttBody precedes this kernel).
+struct StoreModDownGalois {
+  static constexpr bool kLoad = false, kStore = true, kGroupOut = false;
+  const u64 *sp;
+  u64 *c1, *g1;
+  D2 ninv, isp;
+  double q, qinv, qsp, half_sp, half_i;
+  u64 qu;
+  u32 elt, nmask;
+  int logn;
+  HD double load(int) const { return 0.0; }
+  HD void group_out(int, const double *) const {}
+  HD void store(int j, double v) const {
+    const double x = f_mulmod_const(v, ninv, q);
+    double t = f_add(u_to_f(sp[j]), half_sp);
+    if (t >= qsp) t = f_add(t, -qsp);
+    const double y = f_add(f_add(x, -t), half_i);  // |y| <= 1.4q + q_sp + q/2 < 5q
+    const u64 c = f_canonical(f_mulmod_const(y, isp, q), q, qinv);
+    c1[j] = c;
+    const u32 raw = static_cast<u32>(j) * elt;
+    g1[raw & nmask] = ((raw >> logn) & 1) && c ? qu - c : c;
+  }
+};
+
+template <int LOGS>
+struct InttModDownBody {
+  static constexpr const char *kName = "intt_moddown";
+  const u64 *acc;  // [items][2][K][N]: [1][i<L] NTT form, [1][K-1] coefficient form
+  u64 *c1;         // [items][L][N] coefficient form
+  u64 *g1;         // [items][L][N] Galois image of c1
+  const DevConsts *C;
+  TwRef tw;
+  u32 elt;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    const int L = C->L, K = C->K, i = bid % L;
+    const size_t item = bid / L;
+    const u64 *src = acc + ((item * 2 + 1) * K + i) * S;
+    const u64 *sp = acc + ((item * 2 + 1) * K + (K - 1)) * S;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[i], qi = C->qinvf[i];
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
+    }
+    SYNC();
+    const size_t o = (item * L + i) * S;
+    const StoreModDownGalois st{sp, c1 + o, g1 + o, C->n_inv_f[i], C->inv_sp_f[i], qd, qi, C->qf[K - 1], static_cast<double>(C->half_sp),
+                                static_cast<double>(C->half_sp_mod_q[i]), C->mod[i].q, elt, static_cast<u32>(S - 1), LOGS};
+    ntt_inv_core_f64<LOGS, 0>(fm, tw.inv_f(i), qd, qi, 0, nt, st);
   }
 };
 

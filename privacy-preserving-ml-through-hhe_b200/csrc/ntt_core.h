@@ -163,11 +163,19 @@ HD void ntt_inv_core(u64 *sm, const W2 *__restrict__ tw, u64 q, u32 mc, int nt) 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// FP64-pipe variants (q <= 2^49, see modarith_f64.h). Shared memory holds doubles (signed integers, |x| <= 4q).
+// FP64-pipe variants (q <= 2^49, see modarith_f64.h). Shared memory holds doubles (signed integers, |x| < 16q <= 2^53).
 //
-// Twiddles are plain doubles w (8 bytes); w/q is formed on the fly as w * (1/q) (one DMUL, relative error <= 2^-52), which
-// keeps the quotient estimate within 1 of the true quotient for |b| <= 4q, so |w*b mod q| <= q: bounds below are in units
-// of q, a forward stage adds at most 1, an inverse stage doubles.
+// Twiddles are plain doubles w (8 bytes); the quotient of a butterfly product is estimated from the product itself
+// (f_mulmod_var: rint(RN(b*w) * (1/q))), so no w/q table is needed.
+//
+// Bound discipline (compile-time, in units of q/16): a product with an operand of magnitude beta*q has magnitude
+// <= (1/2 + 3 beta 2^-53 2^49) q = (1/2 + 0.1875 beta) q (f64_tbound16), a forward stage adds that to every residue, an
+// inverse stage doubles the sums. Every intermediate must stay below 16q (exact integers in a double); the chains
+// below keep it under 12q. A forward register pass runs in one of two modes:
+//   kNone  no reduction at all
+//   kHalf  the four "a" inputs of the pass's last stage (the residues that are not multiplied there) are reduced to
+//          |x| <= q/2 + 1 first, so the pass's outputs are bounded by q/2 + one product whatever came in.
+// Inverse passes reduce every residue on load (three doublings follow).
 //
 // Two table layouts per (modulus, direction), both of N doubles (F64Tw):
 //   idx[k]          index-major, SEAL's order (psi^bitrev(k)): used by passes whose twiddles are warp-uniform
@@ -185,6 +193,23 @@ HD size_t f64tw_offset(int g0, int gmin) {
   return off;
 }
 
+// bound (units of q/16) of a product whose variable operand is bounded by b16, with one unit of slack
+constexpr int f64_tbound16(int b16) { return 8 + (3 * b16 + 15) / 16 + 1; }
+constexpr int kF64Reduced16 = 9;   // q/2 + 1
+constexpr int kF64PassLimit16 = 120;  // a pass may leave at most 7.5q to the next one (a kHalf pass then peaks below 12q)
+constexpr int kF64AnyOut16 = 160;     // what f_canonical / f_reduce callers accept from a transform
+enum F64Mode { kNone = 0, kHalf = 1, kFull = 2 };
+// output bound of a forward pass of R stages entered with bound b16
+constexpr int f64_fwd_out16(int b16, int R, bool half) {
+  for (int s = 0; s < R; ++s) b16 = ((half && s == R - 1) ? kF64Reduced16 : b16) + f64_tbound16(b16);
+  return b16;
+}
+// largest intermediate of a kHalf pass: the residues entering its last stage (operands of that stage's products)
+constexpr int f64_fwd_peak16(int b16, int R) {
+  for (int s = 0; s + 1 < R; ++s) b16 += f64_tbound16(b16);
+  return b16;
+}
+
 // Register pass over local stages [S0, S0+R) of chunk `chunk` of a transform that was split into 2^LM chunks.
 // Every stride is a compile-time constant, so shared-memory and twiddle accesses use immediate offsets.
 // IO: optional global-memory side of the pass. The forward transform's first pass (S0 == 0) can take its inputs from
@@ -200,8 +225,8 @@ struct SmemIO {
   HD void group_out(int, const double *) const {}
 };
 
-template <int R, bool INVERSE, int LOGS, int S0, int LM, class IO = SmemIO>
-HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, bool reduce, const IO &io = IO()) {
+template <int R, bool INVERSE, int LOGS, int S0, int LM, int MODE, class IO = SmemIO>
+HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, const IO &io = IO()) {
   constexpr int E = 1 << R;
   constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
   constexpr int G0 = S0 + LM;        // global stage of the pass
@@ -228,7 +253,7 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   double x[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) x[e] = kGlobalIn ? io.load((hi << (LOGS - S0)) + lo + (e << LG)) : sm[a0 + off(e)];
-  if (reduce) {
+  if (MODE == kFull) {
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = f_reduce(x[e], q, qinv);
   }
@@ -236,13 +261,17 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
 #pragma unroll
     for (int d = 0; d < R; ++d) {
       const int half = E >> (d + 1);
+      if (MODE == kHalf && d == R - 1) {
+#pragma unroll
+        for (int e = 0; e < E; e += 2) x[e] = f_reduce(x[e], q, qinv);
+      }
 #pragma unroll
       for (int j = 0; j < (1 << d); ++j) {
-        const D2 w{wv[(1 << d) + j], f_mul(wv[(1 << d) + j], qinv)};
+        const double w = wv[(1 << d) + j];
 #pragma unroll
         for (int k = 0; k < half; ++k) {
           double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
-          const double t = f_mulmod_const(b, w, q);
+          const double t = f_mulmod_var(b, w, q, qinv);
           b = f_add(a, -t);
           a = f_add(a, t);
         }
@@ -254,13 +283,13 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
       const int half = E >> (d + 1);
 #pragma unroll
       for (int j = 0; j < (1 << d); ++j) {
-        const D2 w{wv[(1 << d) + j], f_mul(wv[(1 << d) + j], qinv)};
+        const double w = wv[(1 << d) + j];
 #pragma unroll
         for (int k = 0; k < half; ++k) {
           double &a = x[2 * j * half + k], &b = x[2 * j * half + k + half];
           const double dlt = f_add(a, -b);
           a = f_add(a, b);
-          b = f_mulmod_const(dlt, w, q);
+          b = f_mulmod_var(dlt, w, q, qinv);
         }
       }
     }
@@ -278,38 +307,44 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   }
 }
 
-// Compile-time chain of forward passes. B2 = twice the bound (in units of q) of the values entering the pass. A stage
-// adds at most q (|w*b mod q| <= q while |b| <= 4q), and every stage input must stay <= 4q (f_rint_mul), so a pass of R
-// stages may start from a bound of at most 4 - (R - 1); otherwise its values are reduced to q/2 on load.
-template <int LOGS, int LM, int S0, int B2>
+// Compile-time chain of forward passes. B16 = bound (units of q/16) of the values entering the pass; MAXOUT16 = the
+// largest bound the consumer of the transform accepts. A pass runs unreduced (kNone) when what it leaves is within
+// kF64PassLimit16 (MAXOUT16 for the last pass), otherwise in kHalf mode.
+template <int LOGS, int LM, int S0, int B16, int MAXOUT16>
 struct FwdChainF64 {
   static constexpr int R = S0 == 0 ? NttSchedule<LOGS>::kFirst : kRadixLog;
-  static constexpr bool kReduce = B2 + 2 * (R - 1) > 8;
-  static constexpr int kOut = (kReduce ? 1 : B2) + 2 * R;
+  static constexpr bool kLast = S0 + R >= LOGS;
+  static constexpr int kLimit = kLast ? MAXOUT16 : kF64PassLimit16;
+  static constexpr bool kHalfMode = f64_fwd_out16(B16, R, false) > kLimit;
+  static constexpr int kOut = f64_fwd_out16(B16, R, kHalfMode);
+  static_assert(f64_fwd_peak16(B16, R) <= 192, "FP64 transform: intermediate bound above 12q");
+  static_assert(kOut <= kLimit, "FP64 transform: pass output above the consumer's bound");
   template <class IO = SmemIO>
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, false, LOGS, S0, LM, IO>(sm, tw, q, qinv, chunk, g, kReduce, io);
+      for (int g = tid; g < (1 << (LOGS - R)); g += nt)
+        group_f64<R, false, LOGS, S0, LM, kHalfMode ? kHalf : kNone, IO>(sm, tw, q, qinv, chunk, g, io);
     }
     SYNC();
-    if (S0 + R < LOGS) FwdChainF64<LOGS, LM, (S0 + R < LOGS ? S0 + R : 0), (S0 + R < LOGS ? kOut : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
+    if (!kLast) FwdChainF64<LOGS, LM, (kLast ? 0 : S0 + R), (kLast ? 16 : kOut), MAXOUT16>::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
-// Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues). Output <= 4q.
-template <int LOGS, int LM, int B2IN, class IO = SmemIO>
+// Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues).
+// Output bound <= MAXOUT16 / 16 q.
+template <int LOGS, int LM, int B2IN, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16>
 HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
   static_assert(kRadixLog == 3, "FP64 path is written for radix-8 register passes");
-  FwdChainF64<LOGS, LM, 0, B2IN>::run(sm, tw, q, qinv, chunk, nt, io);
+  FwdChainF64<LOGS, LM, 0, B2IN * 8, MAXOUT16>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 // Same, entering the chain at local stage S0 (the caller already performed the stages below S0).
-template <int LOGS, int LM, int S0, int B2IN, class IO = SmemIO>
+template <int LOGS, int LM, int S0, int B2IN, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16>
 HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
-  FwdChainF64<LOGS, LM, S0, B2IN>::run(sm, tw, q, qinv, chunk, nt, io);
+  FwdChainF64<LOGS, LM, S0, B2IN * 8, MAXOUT16>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
-// Inverse passes, highest stages first; every pass reduces on load (3 doublings of q/2: differences stay <= 4q).
+// Inverse passes, highest stages first; every pass reduces on load (q/2 + 1, then three doublings: <= 4.5q).
 template <int LOGS, int LM, int S0>
 struct InvChainF64 {
   template <class IO = SmemIO>
@@ -317,7 +352,7 @@ struct InvChainF64 {
     constexpr int R0 = NttSchedule<LOGS>::kFirst;
     constexpr int R = S0 == 0 ? R0 : kRadixLog;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, true, LOGS, S0, LM, IO>(sm, tw, q, qinv, chunk, g, true, io);
+      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, true, LOGS, S0, LM, kFull, IO>(sm, tw, q, qinv, chunk, g, io);
     }
     SYNC();
     if (S0 > 0) InvChainF64<LOGS, LM, (S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
