@@ -89,6 +89,7 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   for (int k = 0; k < P_.K; ++k) compact_keys_ = compact_keys_ && table_is_f64(P_, k);
   tmem_ks_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_TMEM");
   half_fwd_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_HALF");
+  if (const char *v = std::getenv("HHE_KS_THREADS")) ks_threads_ = std::atoi(v);
   std::vector<W2> tw(ntab * 2 * P_.N);
   for (size_t t = 0; t < ntab; ++t) {
     if (!P_.tab[t].q) continue;
@@ -376,17 +377,24 @@ void Engine::launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, 
                               size_t reuse_stride, const u32 *perm) {
   const int K = P_.K;
   if (tmem_ks_) {
+#ifdef HHE_CUDA
+    const bool emulate = false;
+#else
+    const bool emulate = true;
+#endif
     HHE_DISPATCH_LOG(P_.logn - 1, {
       constexpr int G = (1 << LOGV) / 8;
-      const int nt = std::max(32, std::min(512, G));
-#ifdef HHE_CUDA
-      const bool emulate = false;
-#else
-      const bool emulate = true;
-#endif
-      KsDigitsTmemBody<LOGV> body{target, tstride, reinterpret_cast<const double *>(key), acc, dC_, twref(), static_cast<int>(items),
-                                  reuse, reuse_stride, perm};
-      dev_.launch(body, items * K * 2, nt, KsDigitsTmemBody<LOGV>::smem_bytes(nt, emulate));
+      if (ks_threads_ == 256) {
+        const int nt = std::max(32, std::min(256, G));
+        KsDigitsTmemBody<LOGV, 256> body{target, tstride, reinterpret_cast<const double *>(key), acc, dC_, twref(), static_cast<int>(items),
+                                         reuse, reuse_stride, perm};
+        dev_.launch(body, items * K * 2, nt, KsDigitsTmemBody<LOGV, 256>::smem_bytes(nt, emulate));
+      } else {
+        const int nt = std::max(32, std::min(512, G));
+        KsDigitsTmemBody<LOGV> body{target, tstride, reinterpret_cast<const double *>(key), acc, dC_, twref(), static_cast<int>(items),
+                                    reuse, reuse_stride, perm};
+        dev_.launch(body, items * K * 2, nt, KsDigitsTmemBody<LOGV>::smem_bytes(nt, emulate));
+      }
     });
     return;
   }

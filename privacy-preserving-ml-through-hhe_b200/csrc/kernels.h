@@ -164,17 +164,19 @@ HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int
   SYNC();
 }
 
+// CTA size of the half-limb kernels (one radix-8 group per thread and pass at least, 512 threads at most)
+constexpr int half_threads(int logh, int maxt = 512) { return (1 << logh) / 8 < 32 ? 32 : ((1 << logh) / 8 > maxt ? maxt : (1 << logh) / 8); }
+
 // the register passes that follow fwd_half_load_f64; results in shared memory (or handed to IO::group_out), |.| <= MAXOUT16/16 q
-template <int LOGH, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16>
+template <int LOGH, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16, int MAXT = 512>
 HD void fwd_half_passes_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const IO &io = IO()) {
   constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
+  constexpr int NT = half_threads(LOGH, MAXT);  // every launch of a half-limb kernel uses exactly this CTA size
   if (kFold)
-    ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), kKsFold2, IO, MAXOUT16>(fm, twk, q, qi, h, nt, io);
+    ntt_fwd_core_f64_from<LOGH, 1, (kFold ? 1 : 0), kKsFold2, IO, MAXOUT16, NT>(fm, twk, q, qi, h, nt, io);
   else
-    ntt_fwd_core_f64<LOGH, 1, kKsFold1, IO, MAXOUT16>(fm, twk, q, qi, h, nt, io);
+    ntt_fwd_core_f64<LOGH, 1, kKsFold1, IO, MAXOUT16, NT>(fm, twk, q, qi, h, nt, io);
 }
-
-constexpr int half_threads(int logh) { return (1 << logh) / 8 < 32 ? 32 : ((1 << logh) / 8 > 512 ? 512 : (1 << logh) / 8); }
 
 constexpr int kMaxMapLimbs = 3 * kMaxLimbs;  // size-3 ciphertext in the Bsk base
 struct TabMap {  // limb index inside an item -> NTT table id
@@ -506,10 +508,10 @@ struct KsMacOut {
   }
 };
 
-template <int LOGH>
+template <int LOGH, int MAXT = 512>
 struct KsDigitsTmemBody {
   static constexpr const char *kName = "ks_digits";
-  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  static constexpr int kMaxThreads = MAXT, kMinBlocks = 2;
   const u64 *target;
   size_t stride;
   const double *key;  // group-major FP64 key [L][2][K][N]
@@ -523,7 +525,8 @@ struct KsDigitsTmemBody {
   static constexpr size_t smem_bytes(int nt, bool emulate) {
     return (ntt_smem_words(1 << LOGH) + 2) * 8 + (emulate ? static_cast<size_t>(2) * (1 << LOGH) * 8 : 0) + 0 * nt;
   }
-  HD void operator()(int bid, int nt, unsigned char *smem) const {
+  HD void operator()(int bid, int, unsigned char *smem) const {
+    constexpr int nt = half_threads(LOGH, MAXT);  // the launch uses exactly this CTA size (Engine::launch_ks_digits)
     constexpr int S = 1 << LOGH, G = S / 8;
     const int N = 2 * S;
     const int K = C->K, L = C->L;
@@ -620,10 +623,7 @@ struct KsDigitsTmemBody {
                      double *emu) const {
     constexpr int G = (1 << LOGH) / 8;
     const MacIO io{k0, k1, G, nt, gpt * 2, q, qi, tbase, emu};
-    if (FOLD)
-      ntt_fwd_core_f64_from<LOGH, 1, (FOLD ? 1 : 0), kKsFold2, MacIO, kKsOut16>(fm, twk, q, qi, h, nt, io);
-    else
-      ntt_fwd_core_f64<LOGH, 1, kKsFold1, MacIO, kKsOut16>(fm, twk, q, qi, h, nt, io);
+    fwd_half_passes_f64<LOGH, MacIO, kKsOut16, MAXT>(fm, twk, q, qi, h, nt, io);
   }
 };
 
@@ -1382,7 +1382,8 @@ struct LiftNttHalfBody {
   u64 *out;       // [items][L][N]
   const DevConsts *C;
   TwRef tw;
-  HD void operator()(int bid, int nt, unsigned char *smem) const {
+  HD void operator()(int bid, int, unsigned char *smem) const {
+    constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
     const int h = bid & 1, lb = bid >> 1;
     const int L = C->L, i = lb % L;
@@ -1415,7 +1416,8 @@ struct NttMacHalfBody {
   int comps;
   size_t sum_stride, sum_off;
   u64 *ntt_out;  // optional: NTT_i(ct) itself (canonical), same indexing as ct
-  HD void operator()(int bid, int nt, unsigned char *smem) const {
+  HD void operator()(int bid, int, unsigned char *smem) const {
+    constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
     const int h = bid & 1, lb = bid >> 1;
     const int L = C->L, i = lb % L;
@@ -1467,7 +1469,8 @@ struct Corr0MacHalfBody {
   u64 *sum;           // [items][2][L][N], component 0 updated
   const DevConsts *C;
   TwRef tw;
-  HD void operator()(int bid, int nt, unsigned char *smem) const {
+  HD void operator()(int bid, int, unsigned char *smem) const {
+    constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
     const int h = bid & 1, lb = bid >> 1;
     const int L = C->L, K = C->K, i = lb % L;

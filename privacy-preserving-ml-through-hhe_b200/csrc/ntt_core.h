@@ -187,6 +187,11 @@ struct F64Tw {
   const double *cm;
   int gmin;  // first global stage that has a component-major table (= logN mod 3, or 3 if that is 0)
 };
+constexpr size_t f64tw_offset_c(int g0, int gmin) {
+  size_t off = 0;
+  for (int g = gmin; g < g0; g += 3) off += static_cast<size_t>(7) << g;
+  return off;
+}
 HD size_t f64tw_offset(int g0, int gmin) {
   size_t off = 0;
   for (int g = gmin; g < g0; g += 3) off += static_cast<size_t>(7) << g;
@@ -237,7 +242,9 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   auto off = [](int e) constexpr { return LG >= 4 ? e * ((1 << LG) + (1 << (LG >= 4 ? LG - 4 : 0))) : (e << LG) + (e >> (LG < 4 ? 4 - LG : 0)); };
   double wv[E];
   if (R == 3 && G0 >= 1 && (G0 % 3) == ((LOGS + LM) % 3)) {
-    const double *T = tw.cm + f64tw_offset(G0, tw.gmin) + H;
+    constexpr int kGmin = (LOGS + LM) % 3 ? (LOGS + LM) % 3 : 3;  // == tw.gmin (Engine: logn % 3, or 3), known at compile time here
+    constexpr size_t kOff = f64tw_offset_c(G0, kGmin);
+    const double *T = tw.cm + kOff + H;
 #pragma unroll
     for (int c = 0; c < E - 1; ++c) wv[c + 1] = T[static_cast<size_t>(c) << G0];
   } else {
@@ -310,7 +317,8 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
 // Compile-time chain of forward passes. B16 = bound (units of q/16) of the values entering the pass; MAXOUT16 = the
 // largest bound the consumer of the transform accepts. A pass runs unreduced (kNone) when what it leaves is within
 // kF64PassLimit16 (MAXOUT16 for the last pass), otherwise in kHalf mode.
-template <int LOGS, int LM, int S0, int B16, int MAXOUT16>
+// NT > 0: the CTA size is known at compile time (the group loops unroll, index arithmetic folds).
+template <int LOGS, int LM, int S0, int B16, int MAXOUT16, int NT = 0>
 struct FwdChainF64 {
   static constexpr int R = S0 == 0 ? NttSchedule<LOGS>::kFirst : kRadixLog;
   static constexpr bool kLast = S0 + R >= LOGS;
@@ -321,27 +329,29 @@ struct FwdChainF64 {
   static_assert(kOut <= kLimit, "FP64 transform: pass output above the consumer's bound");
   template <class IO = SmemIO>
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
+    const int st = NT ? NT : nt;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R)); g += nt)
+#pragma unroll
+      for (int g = tid; g < (1 << (LOGS - R)); g += st)
         group_f64<R, false, LOGS, S0, LM, kHalfMode ? kHalf : kNone, IO>(sm, tw, q, qinv, chunk, g, io);
     }
     SYNC();
-    if (!kLast) FwdChainF64<LOGS, LM, (kLast ? 0 : S0 + R), (kLast ? 16 : kOut), MAXOUT16>::run(sm, tw, q, qinv, chunk, nt, io);
+    if (!kLast) FwdChainF64<LOGS, LM, (kLast ? 0 : S0 + R), (kLast ? 16 : kOut), MAXOUT16, NT>::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
 // Forward transform on doubles. B2IN = twice the input bound in units of q (2 for canonical residues).
 // Output bound <= MAXOUT16 / 16 q.
-template <int LOGS, int LM, int B2IN, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16>
+template <int LOGS, int LM, int B2IN, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16, int NT = 0>
 HD void ntt_fwd_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
   static_assert(kRadixLog == 3, "FP64 path is written for radix-8 register passes");
-  FwdChainF64<LOGS, LM, 0, B2IN * 8, MAXOUT16>::run(sm, tw, q, qinv, chunk, nt, io);
+  FwdChainF64<LOGS, LM, 0, B2IN * 8, MAXOUT16, NT>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 // Same, entering the chain at local stage S0 (the caller already performed the stages below S0).
-template <int LOGS, int LM, int S0, int B2IN, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16>
+template <int LOGS, int LM, int S0, int B2IN, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16, int NT = 0>
 HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
-  FwdChainF64<LOGS, LM, S0, B2IN * 8, MAXOUT16>::run(sm, tw, q, qinv, chunk, nt, io);
+  FwdChainF64<LOGS, LM, S0, B2IN * 8, MAXOUT16, NT>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 // Inverse passes, highest stages first; every pass reduces on load (q/2 + 1, then three doublings: <= 4.5q).
