@@ -24,6 +24,10 @@
 #define SYNC() ((void)0)
 #endif
 
+#ifndef HHE_MAX_THREADS
+#define HHE_MAX_THREADS 1024
+#endif
+
 namespace hhe {
 using u32 = uint32_t;
 using u64 = uint64_t;

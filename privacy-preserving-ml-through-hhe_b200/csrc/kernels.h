@@ -164,6 +164,9 @@ HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int
   SYNC();
 }
 
+// CTA size of the whole-limb kernels (Engine: ntt_threads)
+constexpr int whole_threads(int logs) { return (1 << logs) / 8 < 32 ? 32 : ((1 << logs) / 8 > HHE_MAX_THREADS ? HHE_MAX_THREADS : (1 << logs) / 8); }
+
 // CTA size of the half-limb kernels (one radix-8 group per thread and pass at least, 512 threads at most)
 constexpr int half_threads(int logh, int maxt = 512) { return (1 << logh) / 8 < 32 ? 32 : ((1 << logh) / 8 > maxt ? maxt : (1 << logh) / 8); }
 
@@ -210,7 +213,7 @@ struct NttBody {
       double *fm = reinterpret_cast<double *>(smem);
       const double qd = C->qf[tab], qi = C->qinvf[tab];
       if (!inverse) {
-        ntt_fwd_core_f64<LOGS, 0, 2>(fm, tw.fwd_f(tab), qd, qi, 0, nt, LoadU64{src});
+        ntt_fwd_core_f64<LOGS, 0, 2, LoadU64, kF64AnyOut16, whole_threads(LOGS)>(fm, tw.fwd_f(tab), qd, qi, 0, nt, LoadU64{src});
         FOR_THREADS(tid, nt) {
           for (int i = tid; i < S; i += nt) dst[i] = f_canonical(fm[pidx(i)], qd, qi);
         }
@@ -219,7 +222,7 @@ struct NttBody {
           for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(src[i]);
         }
         SYNC();
-        ntt_inv_core_f64<LOGS, 0>(fm, tw.inv_f(tab), qd, qi, 0, nt, StoreScaled{dst, C->n_inv_f[tab], qd, qi});
+        ntt_inv_core_f64<LOGS, 0, StoreScaled, whole_threads(LOGS)>(fm, tw.inv_f(tab), qd, qi, 0, nt, StoreScaled{dst, C->n_inv_f[tab], qd, qi});
       }
       return;
     }
@@ -1572,7 +1575,7 @@ struct InttModDownBody {
     const size_t o = (item * L + i) * S;
     const StoreModDownGalois st{sp, c1 + o, g1 + o, C->n_inv_f[i], C->inv_sp_f[i], qd, qi, C->qf[K - 1], static_cast<double>(C->half_sp),
                                 static_cast<double>(C->half_sp_mod_q[i]), C->mod[i].q, elt, static_cast<u32>(S - 1), LOGS};
-    ntt_inv_core_f64<LOGS, 0>(fm, tw.inv_f(i), qd, qi, 0, nt, st);
+    ntt_inv_core_f64<LOGS, 0, StoreModDownGalois, whole_threads(LOGS)>(fm, tw.inv_f(i), qd, qi, 0, nt, st);
   }
 };
 

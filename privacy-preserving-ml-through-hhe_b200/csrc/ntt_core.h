@@ -314,6 +314,29 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   }
 }
 
+// Synchronisation between two consecutive register passes. The groups g in [hi * 2^LGDOM, (hi + 1) * 2^LGDOM) of the
+// producing pass write exactly the residues that the same range of groups of the consuming pass reads (LGDOM = the larger
+// element-stride exponent of the two passes), and group g belongs to thread g mod NT. When the CTA size NT is known at
+// compile time only those 2^LGDOM threads have to meet: a warp-level sync for <= 32 threads, a named barrier for a
+// few warps, the CTA barrier otherwise.
+template <int LGDOM, int NT>
+HD void sync_domain() {
+#if defined(__CUDA_ARCH__)
+#if defined(HHE_FULL_BARRIERS)
+  if constexpr (true) {
+#else
+  if constexpr (NT == 0 || (1 << LGDOM) >= NT || (NT >> LGDOM) > 15) {
+#endif
+    __syncthreads();
+  } else if constexpr (LGDOM <= 5) {
+    __syncwarp();
+  } else {
+    const unsigned id = 1u + (threadIdx.x >> LGDOM);
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(1u << LGDOM) : "memory");
+  }
+#endif
+}
+
 // Compile-time chain of forward passes. B16 = bound (units of q/16) of the values entering the pass; MAXOUT16 = the
 // largest bound the consumer of the transform accepts. A pass runs unreduced (kNone) when what it leaves is within
 // kF64PassLimit16 (MAXOUT16 for the last pass), otherwise in kHalf mode.
@@ -335,7 +358,10 @@ struct FwdChainF64 {
       for (int g = tid; g < (1 << (LOGS - R)); g += st)
         group_f64<R, false, LOGS, S0, LM, kHalfMode ? kHalf : kNone, IO>(sm, tw, q, qinv, chunk, g, io);
     }
-    SYNC();
+    if (kLast)
+      SYNC();
+    else
+      sync_domain<LOGS - S0 - R, NT>();  // this pass's element stride is the larger one
     if (!kLast) FwdChainF64<LOGS, LM, (kLast ? 0 : S0 + R), (kLast ? 16 : kOut), MAXOUT16, NT>::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
@@ -355,26 +381,32 @@ HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int c
 }
 
 // Inverse passes, highest stages first; every pass reduces on load (q/2 + 1, then three doublings: <= 4.5q).
-template <int LOGS, int LM, int S0>
+template <int LOGS, int LM, int S0, int NT = 0>
 struct InvChainF64 {
   template <class IO = SmemIO>
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
     constexpr int R0 = NttSchedule<LOGS>::kFirst;
     constexpr int R = S0 == 0 ? R0 : kRadixLog;
+    constexpr int kNext = S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0;  // first stage of the pass that consumes this one
+    const int st = NT ? NT : nt;
     FOR_THREADS(tid, nt) {
-      for (int g = tid; g < (1 << (LOGS - R)); g += nt) group_f64<R, true, LOGS, S0, LM, kFull, IO>(sm, tw, q, qinv, chunk, g, io);
+#pragma unroll
+      for (int g = tid; g < (1 << (LOGS - R)); g += st) group_f64<R, true, LOGS, S0, LM, kFull, IO>(sm, tw, q, qinv, chunk, g, io);
     }
-    SYNC();
-    if (S0 > 0) InvChainF64<LOGS, LM, (S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
+    if (S0 == 0)
+      SYNC();
+    else
+      sync_domain<LOGS - kNext - (kNext == 0 ? R0 : kRadixLog), NT>();  // the consumer's element stride is the larger one
+    if (S0 > 0) InvChainF64<LOGS, LM, kNext, NT>::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
 // Inverse transform on doubles (without 1/N unless the IO functor applies it). With a storing IO functor the results
 // leave through IO::store and shared memory holds garbage afterwards.
-template <int LOGS, int LM, class IO = SmemIO>
+template <int LOGS, int LM, class IO = SmemIO, int NT = 0>
 HD void ntt_inv_core_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
   constexpr int R0 = NttSchedule<LOGS>::kFirst;
-  InvChainF64<LOGS, LM, (LOGS - kRadixLog >= R0 ? LOGS - kRadixLog : 0)>::run(sm, tw, q, qinv, chunk, nt, io);
+  InvChainF64<LOGS, LM, (LOGS - kRadixLog >= R0 ? LOGS - kRadixLog : 0), NT>::run(sm, tw, q, qinv, chunk, nt, io);
 }
 
 }  // namespace hhe

@@ -47,6 +47,8 @@ struct TmemAcc {
         : "r"(addr0 + static_cast<u32>(slot) * 16u), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
           "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
+    // the wait is needed right here: deferring it to the next access of the slot gave wrong sums on B200 (the source
+    // registers are evidently read asynchronously), see DESIGN.md
     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
   }
 #else
