@@ -19,9 +19,11 @@
 #if defined(__CUDA_ARCH__)
 #define FOR_THREADS(tid, nt) for (int tid = threadIdx.x, hhe_once_ = 1; hhe_once_; hhe_once_ = 0)
 #define SYNC() __syncthreads()
+#define SYNCWARP() __syncwarp()
 #else
 #define FOR_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
 #define SYNC() ((void)0)
+#define SYNCWARP() ((void)0)
 #endif
 
 #ifndef HHE_MAX_THREADS

@@ -103,7 +103,12 @@ struct RawCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[speci
   }
 };
 
-template <int LOGH, class LD>
+// With WARP_LOCAL (CTA of NT = S/16 threads, two folded stages) warp w folds the residues i, i + S/2 with
+// i in [256 w, 256 w + 256): exactly the residues its own threads read in the LAST register pass of the previous
+// transform that used the same buffer, so back-to-back transforms need only a warp-level sync in between.
+constexpr bool half_warp_local(int logh, int nt) { return NttSchedule_first(logh) == 1 && nt * 16 == (1 << logh); }
+
+template <int LOGH, class LD, bool WARP_LOCAL = false>
 HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const LD &ld) {
   constexpr int S = 1 << LOGH;
   constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
@@ -111,17 +116,21 @@ HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int
   if (kFold) {
     const D2 w2{twk.idx[2 + h], f_mul(twk.idx[2 + h], qi)};
     FOR_THREADS(tid, nt) {
-      // software pipeline: the four loads of iteration n+1 are in flight while iteration n is computed
+      // thread's residues: first + k * step; software pipeline: the four loads of iteration n+1 are in flight while
+      // iteration n is computed
+      const int first = WARP_LOCAL ? ((tid >> 5) << 8) + (tid & 31) : tid;
+      const int step = WARP_LOCAL ? 32 : nt;
+      const int count = WARP_LOCAL ? 8 : (S / 2 - tid + nt - 1) / nt;
       u64 v[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0};
-      if (tid < S / 2) {
-        v[0] = ld.raw(tid);
-        v[1] = ld.raw(tid + S);
-        v[2] = ld.raw(tid + S / 2);
-        v[3] = ld.raw(tid + S / 2 + S);
+      if (count > 0) {
+        v[0] = ld.raw(first);
+        v[1] = ld.raw(first + S);
+        v[2] = ld.raw(first + S / 2);
+        v[3] = ld.raw(first + S / 2 + S);
       }
-      for (int i = tid; i < S / 2; i += nt) {
-        const int in = i + nt;
-        if (in < S / 2) {
+      for (int k = 0; k < count; ++k) {
+        const int i = first + k * step, in = i + step;
+        if (k + 1 < count) {
           nv[0] = ld.raw(in);
           nv[1] = ld.raw(in + S);
           nv[2] = ld.raw(in + S / 2);
@@ -542,6 +551,7 @@ struct KsDigitsTmemBody {
     const double q = C->qf[k], qi = C->qinvf[k];
     const F64Tw twk = tw.fwd_f(k);
     constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
+    constexpr bool kWarpLocal = half_warp_local(LOGH, nt);
     u32 tbase = 0;
 #if defined(__CUDA_ARCH__)
     const int ncols = tmem_columns(nt, gpt * 2);
@@ -576,11 +586,16 @@ struct KsDigitsTmemBody {
         continue;
       }
       const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
-      fwd_half_load_f64<LOGH>(fm, twk, q, qi, h, nt, RawU64{dig});  // ends with a barrier
+      fwd_half_load_f64<LOGH, RawU64, kWarpLocal>(fm, twk, q, qi, h, nt, RawU64{dig});  // ends with a barrier
       // register passes; the last one hands its outputs to KsMacOut::group_out. The functor is rebuilt per thread inside
       // the chain's FOR_THREADS through TmemAcc::make, so pass the ingredients.
       run_passes<kFold>(fm, twk, q, qi, h, nt, k0, k1, tbase, gpt, emu);
-      SYNC();  // the next digit's load overwrites fm
+      // the next digit's load (or the write-out) overwrites fm: with the warp-local fold it touches only residues this warp
+      // itself read in the last pass
+      if (kWarpLocal)
+        SYNCWARP();
+      else
+        SYNC();
     }
     // write-out: TMEM -> canonical residues -> global (through shared memory so that stores are coalesced)
     u64 *fo = reinterpret_cast<u64 *>(fm);

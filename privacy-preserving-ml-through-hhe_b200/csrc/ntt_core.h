@@ -20,6 +20,11 @@ namespace hhe {
 // Shared-memory index padding: one extra word per 16 keeps the stride-16/stride-1 mixes of the register passes
 // spread over the banks.
 HD int pidx(int i) { return i + (i >> 4); }
+// A pass whose element stride is 8 (lg == 3) would put lanes 0-7 and 8-15 of a half warp on overlapping banks (their
+// 64-residue blocks are 4 padded words apart): exchanging bits 3 and 4 of the group index inside each warp pairs blocks
+// that are 8 words apart instead. A bijection on the groups of a warp, so nothing else changes (tools: /tmp-free check
+// in DESIGN.md; ncu: 22% of the shared-memory wavefronts were conflict replays before).
+HD int stride8_group(int g) { return (g & ~0x18) | ((g & 8) << 1) | ((g & 16) >> 1); }
 constexpr size_t ntt_smem_words(int S) { return static_cast<size_t>(S) + (S >> 4); }
 
 HD void fwd_bfly(u64 &a, u64 &b, W2 w, u64 q, u64 two_q) {
@@ -47,6 +52,7 @@ template <int R, bool WIDE = false>
 HD void fwd_group(u64 *sm, const W2 *__restrict__ tw, u64 q, int logS, int s0, u32 mc, int g) {
   constexpr int E = 1 << R;
   const int lg = logS - s0 - R;
+  if (lg == 3) g = stride8_group(g);
   const int lo = g & ((1 << lg) - 1), hi = g >> lg;
   const int base = (hi << (logS - s0)) + lo;
   const u64 two_q = q << 1, nq = 0 - q, four_q = q << 2;
@@ -84,6 +90,7 @@ template <int R>
 HD void inv_group(u64 *sm, const W2 *__restrict__ tw, u64 q, int logS, int s0, u32 mc, int g) {
   constexpr int E = 1 << R;
   const int lg = logS - s0 - R;
+  if (lg == 3) g = stride8_group(g);
   const int lo = g & ((1 << lg) - 1), hi = g >> lg;
   const int base = (hi << (logS - s0)) + lo;
   const u64 two_q = q << 1;
@@ -109,6 +116,7 @@ HD void inv_group(u64 *sm, const W2 *__restrict__ tw, u64 q, int logS, int s0, u
 #define HHE_RADIX_LOG 3
 #endif
 constexpr int kRadixLog = HHE_RADIX_LOG;  // stages per register pass (4: radix-16, 3: radix-8)
+constexpr int NttSchedule_first(int logs) { return logs - kRadixLog * ((logs - 1) / kRadixLog); }
 template <int LOGS>
 struct NttSchedule {
   static constexpr int kFirst = LOGS - kRadixLog * ((LOGS - 1) / kRadixLog);  // stages in the odd-sized pass
@@ -235,6 +243,7 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   constexpr int E = 1 << R;
   constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
   constexpr int G0 = S0 + LM;        // global stage of the pass
+  if (LG == 3) g = stride8_group(g);
   const int lo = g & ((1 << LG) - 1), hi = g >> LG;
   const int H = (chunk << S0) + hi;  // global block index at stage G0
   // padded shared-memory offsets: pidx(base + (e << LG)) = a0 + off(e) with compile-time off(e)
