@@ -368,6 +368,19 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
   } else {
     launch_ks_digits(target, tstride, key, acc, items, nullptr, 0, nullptr);
   }
+  if (compact_keys_ && !split_) {
+    // FP64 path: the two special limbs first, then the data limbs with ModDown + add fused into the transform's store
+    TabMap msp2{};
+    msp2.id[0] = msp2.id[1] = static_cast<unsigned char>(K - 1);
+    const size_t N = P_.N;
+    ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, items, 2, msp2, true, static_cast<size_t>(2) * K * N,
+        static_cast<size_t>(K) * N);
+    HHE_DISPATCH_LOG(P_.logn, {
+      InttModDownAddBody<LOGV> body{acc, base0, base1, bstride, out, dC_, twref()};
+      dev_.launch(body, items * 2 * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    return;
+  }
   ntt(acc, acc, items, 2 * K, map_mod(2 * K, K, 0), true);
   ModDownBody md{acc, base0, base1, bstride, out, dC_, items * P_.N};
   dev_.launch(md, ew_grid(items * P_.N), kEwThreads, 0);

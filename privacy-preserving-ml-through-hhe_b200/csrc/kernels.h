@@ -1594,6 +1594,59 @@ struct InttModDownBody {
   }
 };
 
+// Generic key switch (rotate / relinearize outside the resident chain), FP64 path: inverse NTT of the accumulator limbs
+// acc[c][i < L] with the rounding ModDown and the final add fused into the store. CTA per (item, component c, limb i):
+//   out[c][i][j] = base_c[i][j] + (INTT(acc[c][i])[j] - ((r_c[j] + half) mod q_sp) + half_i) * q_sp^-1  mod q_i
+// r_c = acc[c][special] must already be in coefficient form (a two-limb launch of NttBody precedes this kernel).
+struct StoreModDownAdd {
+  static constexpr bool kLoad = false, kStore = true, kGroupOut = false;
+  const u64 *sp, *base;
+  u64 *out;
+  D2 ninv, isp;
+  double q, qinv, qsp, half_sp, half_i;
+  HD double load(int) const { return 0.0; }
+  HD void group_out(int, const double *) const {}
+  HD void store(int j, double v) const {
+    const double x = f_mulmod_const(v, ninv, q);
+    double t = f_add(u_to_f(sp[j]), half_sp);
+    if (t >= qsp) t = f_add(t, -qsp);
+    const double y = f_add(f_add(x, -t), half_i);  // |y| < 5q
+    double c = f_mulmod_const(y, isp, q);          // |c| <= 1.5q
+    if (base) c = f_add(c, u_to_f(base[j]));
+    out[j] = f_canonical(c, q, qinv);
+  }
+};
+
+template <int LOGS>
+struct InttModDownAddBody {
+  static constexpr const char *kName = "intt_moddown";
+  const u64 *acc;    // [items][2][K][N]
+  const u64 *base0;  // item b at base0 + b*bstride : [L][N] (may be null)
+  const u64 *base1;
+  size_t bstride;
+  u64 *out;  // [items][2][L][N]
+  const DevConsts *C;
+  TwRef tw;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int S = 1 << LOGS;
+    const int L = C->L, K = C->K, i = bid % L, c = (bid / L) & 1;
+    const size_t item = bid / (2 * L);
+    const u64 *src = acc + ((item * 2 + c) * K + i) * S;
+    const u64 *sp = acc + ((item * 2 + c) * K + (K - 1)) * S;
+    const u64 *bs = c ? base1 : base0;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[i], qi = C->qinvf[i];
+    FOR_THREADS(tid, nt) {
+      for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
+    }
+    SYNC();
+    const StoreModDownAdd st{sp, bs ? bs + item * bstride + static_cast<size_t>(i) * S : nullptr, out + ((item * 2 + c) * L + i) * S,
+                             C->n_inv_f[i], C->inv_sp_f[i], qd, qi, C->qf[K - 1], static_cast<double>(C->half_sp),
+                             static_cast<double>(C->half_sp_mod_q[i])};
+    ntt_inv_core_f64<LOGS, 0, StoreModDownAdd, whole_threads(LOGS)>(fm, tw.inv_f(i), qd, qi, 0, nt, st);
+  }
+};
+
 // value -> (value, floor(value * 2^64 / q)) for uploaded key-switching keys (one-time, at hhe_load_ksk)
 struct ShoupifyBody {
   static constexpr const char *kName = "shoupify";
