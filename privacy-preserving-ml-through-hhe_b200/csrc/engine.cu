@@ -90,6 +90,7 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   tmem_ks_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_TMEM");
   half_fwd_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_HALF");
   if (const char *v = std::getenv("HHE_KS_THREADS")) ks_threads_ = std::atoi(v);
+  cluster_inv_ = half_fwd_ && !getenv_flag("HHE_NO_CLUSTER");
   std::vector<W2> tw(ntab * 2 * P_.N);
   for (size_t t = 0; t < ntab; ++t) {
     if (!P_.tab[t].q) continue;
@@ -224,6 +225,20 @@ void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap 
       dev_.launch(fin, ew_grid(total), kEwThreads, 0);
     }
     return;
+  }
+  if (inverse && cluster_inv_) {
+    bool all_f64 = true;
+    for (int l = 0; l < limbs; ++l) all_f64 = all_f64 && table_is_f64(P_, map.id[l]);
+    if (all_f64) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        using Body = InvClusterBody<LOGV, PlanScaled>;
+        Body body{PlanScaled{in, out, map, limbs, item_stride ? item_stride : static_cast<size_t>(limbs) << (LOGV + 1),
+                             limb_stride ? limb_stride : static_cast<size_t>(2) << LOGV},
+                  dC_, twref()};
+        dev_.launch_cluster2(body, items * limbs * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+      return;
+    }
   }
   HHE_DISPATCH_LOG(P_.logn, {
     NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, item_stride ? item_stride : static_cast<size_t>(limbs) << LOGV,
@@ -375,6 +390,14 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
     const size_t N = P_.N;
     ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, items, 2, msp2, true, static_cast<size_t>(2) * K * N,
         static_cast<size_t>(K) * N);
+    if (cluster_inv_) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        using Body = InvClusterBody<LOGV, PlanModDownAdd>;
+        Body body{PlanModDownAdd{acc, base0, base1, bstride, out}, dC_, twref()};
+        dev_.launch_cluster2(body, items * 2 * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+      return;
+    }
     HHE_DISPATCH_LOG(P_.logn, {
       InttModDownAddBody<LOGV> body{acc, base0, base1, bstride, out, dC_, twref()};
       dev_.launch(body, items * 2 * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -591,10 +614,18 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     // with the ModDown and the next rotation's Galois map fused into the store
     ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, 2, msp2, true, static_cast<size_t>(2) * K * N,
         static_cast<size_t>(K) * N);
-    HHE_DISPATCH_LOG(P_.logn, {
-      InttModDownBody<LOGV> body{acc, c1c, g1, dC_, twref(), e1};
-      dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
-    });
+    if (cluster_inv_) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        using Body = InvClusterBody<LOGV, PlanModDownGalois>;
+        Body body{PlanModDownGalois{acc, c1c, g1, e1, P_.logn}, dC_, twref()};
+        dev_.launch_cluster2(body, nb * L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+    } else {
+      HHE_DISPATCH_LOG(P_.logn, {
+        InttModDownBody<LOGV> body{acc, c1c, g1, dC_, twref(), e1};
+        dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+    }
     encode_material(mat, nullptr, kDiag, layer, i, pt, nb);
     lift_ntt(pt, D, nb);
     if (half_fwd_) {

@@ -1647,6 +1647,111 @@ struct InttModDownAddBody {
   }
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// Inverse transforms as two-CTA clusters (FP64 path). The last Gentleman-Sande stage of an N-point inverse transform
+// pairs residue i with i + N/2; everything before it happens inside the two halves independently. CTA h of a cluster
+// runs the N/2-point sub-transform of half h in its own 68 KiB of shared memory (two CTAs per SM, as for the forward
+// half-limb kernels), the pair meets at a cluster barrier, and each CTA then finishes one quarter of the butterflies of
+// the last stage, reading the partner's half through distributed shared memory. The Plan supplies, per limb, the source,
+// the NTT table and the store functor that receives the (unscaled) outputs: plain scaling, or the fused ModDown variants.
+template <int LOGH, class Plan>
+struct InvClusterBody {
+  static constexpr const char *kName = Plan::kName;
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  Plan plan;
+  const DevConsts *C;
+  TwRef tw;
+  HD void phase1(int bid, int, unsigned char *smem) const {
+    constexpr int S = 1 << LOGH;
+    constexpr int nt = half_threads(LOGH);
+    const int h = bid & 1, lb = bid >> 1;
+    const int tab = plan.tab(lb, C);
+    const u64 *src = plan.src(lb, C, 2 * S) + static_cast<size_t>(h) * S;
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[tab], qi = C->qinvf[tab];
+    FOR_THREADS(tid, nt) {
+#pragma unroll 4
+      for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
+    }
+    SYNC();
+    ntt_inv_core_f64<LOGH, 1, SmemIO, nt>(fm, tw.inv_f(tab), qd, qi, h, nt);
+  }
+  HD void phase2(int bid, int, const unsigned char *smem, const unsigned char *peer) const {
+    constexpr int S = 1 << LOGH;
+    constexpr int nt = half_threads(LOGH);
+    const int h = bid & 1, lb = bid >> 1;
+    const int tab = plan.tab(lb, C);
+    const double qd = C->qf[tab], qi = C->qinvf[tab];
+    const double *lo = reinterpret_cast<const double *>(h ? peer : smem);  // residues [0, S) of the limb
+    const double *hi = reinterpret_cast<const double *>(h ? smem : peer);  // residues [S, 2S)
+    const double w = tw.inv_f(tab).idx[1];
+    const auto st = plan.store(lb, C, 2 * S);
+    FOR_THREADS(tid, nt) {
+#pragma unroll 2
+      for (int j = h * (S / 2) + tid; j < (h + 1) * (S / 2); j += nt) {
+        const double a = lo[pidx(j)], b = hi[pidx(j)];  // |.| <= 4.5q
+        st.store(j, f_add(a, b));
+        st.store(j + S, f_mulmod_var(f_add(a, -b), w, qd, qi));
+      }
+    }
+  }
+};
+
+struct PlanScaled {  // NttBody's inverse branch: out = INTT(in) (scaled by 1/N, canonical)
+  static constexpr const char *kName = "ntt";
+  const u64 *in;
+  u64 *out;
+  TabMap map;
+  int limbs;
+  size_t istride, lstride;
+  HD int tab(int lb, const DevConsts *) const { return map.id[lb % limbs]; }
+  HD size_t at(int lb) const { return static_cast<size_t>(lb / limbs) * istride + static_cast<size_t>(lb % limbs) * lstride; }
+  HD const u64 *src(int lb, const DevConsts *, int) const { return in + at(lb); }
+  HD StoreScaled store(int lb, const DevConsts *C, int) const {
+    const int t = tab(lb, C);
+    return StoreScaled{out + at(lb), C->n_inv_f[t], C->qf[t], C->qinvf[t]};
+  }
+};
+struct PlanModDownGalois {  // InttModDownBody
+  static constexpr const char *kName = "intt_moddown";
+  const u64 *acc;
+  u64 *c1, *g1;
+  u32 elt;
+  int logn;
+  HD int tab(int lb, const DevConsts *C) const { return lb % C->L; }
+  HD const u64 *src(int lb, const DevConsts *C, int N) const {
+    const size_t item = lb / C->L;
+    return acc + ((item * 2 + 1) * C->K + lb % C->L) * N;
+  }
+  HD StoreModDownGalois store(int lb, const DevConsts *C, int N) const {
+    const int L = C->L, K = C->K, i = lb % L;
+    const size_t item = lb / L, o = (item * L + i) * N;
+    return StoreModDownGalois{acc + ((item * 2 + 1) * K + (K - 1)) * N, c1 + o, g1 + o, C->n_inv_f[i], C->inv_sp_f[i], C->qf[i], C->qinvf[i],
+                              C->qf[K - 1], static_cast<double>(C->half_sp), static_cast<double>(C->half_sp_mod_q[i]), C->mod[i].q, elt,
+                              static_cast<u32>(N - 1), logn};
+  }
+};
+struct PlanModDownAdd {  // InttModDownAddBody
+  static constexpr const char *kName = "intt_moddown";
+  const u64 *acc, *base0, *base1;
+  size_t bstride;
+  u64 *out;
+  HD int tab(int lb, const DevConsts *C) const { return lb % C->L; }
+  HD const u64 *src(int lb, const DevConsts *C, int N) const {
+    const int L = C->L;
+    const size_t item = lb / (2 * L);
+    return acc + ((item * 2 + ((lb / L) & 1)) * C->K + lb % L) * N;
+  }
+  HD StoreModDownAdd store(int lb, const DevConsts *C, int N) const {
+    const int L = C->L, K = C->K, i = lb % L, c = (lb / L) & 1;
+    const size_t item = lb / (2 * L);
+    const u64 *bs = c ? base1 : base0;
+    return StoreModDownAdd{acc + ((item * 2 + c) * K + (K - 1)) * N, bs ? bs + item * bstride + static_cast<size_t>(i) * N : nullptr,
+                           out + ((item * 2 + c) * L + i) * N, C->n_inv_f[i], C->inv_sp_f[i], C->qf[i], C->qinvf[i], C->qf[K - 1],
+                           static_cast<double>(C->half_sp), static_cast<double>(C->half_sp_mod_q[i])};
+  }
+};
+
 // value -> (value, floor(value * 2^64 / q)) for uploaded key-switching keys (one-time, at hhe_load_ksk)
 struct ShoupifyBody {
   static constexpr const char *kName = "shoupify";

@@ -12,6 +12,7 @@
 #include "hd.h"
 
 #ifdef HHE_CUDA
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #endif
 
@@ -40,6 +41,20 @@ template <class Body>
 __global__ void __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry(const Body body) {
   extern __shared__ __align__(16) unsigned char hhe_smem[];
   body(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
+}
+
+// Two-CTA thread-block cluster: the bodies of a pair run phase1 on their own shared memory, meet at a cluster barrier,
+// then run phase2 with a pointer to the partner's shared memory (distributed shared memory, read-only use).
+template <class Body>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry_c2(const Body body) {
+  extern __shared__ __align__(16) unsigned char hhe_smem[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  body.phase1(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
+  cluster.sync();
+  const unsigned char *peer = cluster.map_shared_rank(hhe_smem, cluster.block_rank() ^ 1u);
+  body.phase2(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem, peer);
+  cluster.sync();  // the partner may still be reading this CTA's shared memory
 }
 #endif
 
@@ -191,6 +206,51 @@ struct Device {
 #else
     std::vector<unsigned char> smem(smem_bytes + 16);
     for (size_t b = 0; b < grid; ++b) body(static_cast<int>(b), nt, smem.data());
+#endif
+  }
+
+  // grid must be even: CTAs 2p and 2p+1 form a cluster (see kernel_entry_c2)
+  template <class Body>
+  void launch_cluster2(const Body &body, size_t grid, int nt, size_t smem_bytes) {
+    if (grid == 0) return;
+    if (grid & 1) throw std::invalid_argument("cluster launch needs an even grid");
+    ++launches;
+    int kid = -1;
+    if (profiling) {
+      kid = kernel_id(Body::kName);
+      ++stats[kid].launches;
+    }
+#ifdef HHE_CUDA
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    if (profiling) {
+      ev_a = get_event();
+      ev_b = get_event();
+      cuda_check(cudaEventRecord(ev_a, stream), "cudaEventRecord");
+    }
+    if (smem_bytes > 48 * 1024) {
+      static size_t configured = 0;  // per Body instantiation
+      if (smem_bytes > configured) {
+        cuda_check(cudaFuncSetAttribute(kernel_entry_c2<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem_bytes)),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        configured = smem_bytes;
+      }
+    }
+    kernel_entry_c2<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
+    cuda_check(cudaGetLastError(), "cluster kernel launch");
+    if (profiling) {
+      cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
+      pending.push_back(Pending{kid, ev_a, ev_b});
+      if (pending.size() >= 8192) profile_resolve();
+    }
+#else
+    std::vector<unsigned char> s0(smem_bytes + 16), s1(smem_bytes + 16);
+    for (size_t b = 0; b < grid; b += 2) {
+      body.phase1(static_cast<int>(b), nt, s0.data());
+      body.phase1(static_cast<int>(b + 1), nt, s1.data());
+      body.phase2(static_cast<int>(b), nt, s0.data(), s1.data());
+      body.phase2(static_cast<int>(b + 1), nt, s1.data(), s0.data());
+    }
 #endif
   }
 };
