@@ -39,6 +39,11 @@ MIB = 1 << 20
 # algorithmic bytes per PASTA-3 block (operands read once + result written once per SEAL-level op)
 BYTES_PER_BLOCK = {False: 7_751_991_296, True: 5_990_383_616}
 KS_BYTES = 4 * MIB  # one key switch (rotate_rows / rotate_columns): 2 ciphertexts
+# FP64-pipe instructions (per thread) ks_digits needs for one item at N=16384: per (key limb, half) CTA
+# 7 digit transforms of 8192 residues (fold 23 x 4096, four radix-8 passes 84 x 1024 each + 3 half reductions 8 x 1024,
+# multiply-accumulate with the key 2 x 6 x 8192) + the digit reused from the plaintext product (13 x 8192) + write-out.
+KS_FP64_PER_ITEM = 18 * (7 * (23 * 4096 + 4 * 84 * 1024 + 3 * 8 * 1024 + 12 * 8192) + 13 * 8192 + 2 * 4 * 8192)
+FP64_LANES_PER_SM_CLK = 64  # DFMA/DMUL/DADD: one warp instruction per 2 cycles per sub-partition (tools/microbench/pipes.cu)
 
 
 def peak_hbm():
@@ -302,6 +307,9 @@ def main():
         # the capture ran at 148 items per launch; DRAM traffic scales with the items of a launch
         traffic = int(ncu["dram_bytes_per_launch_at_capture_batch_148"] * B / 148)
     kernel_ms = sum(v["ms"] for v in prof.values())
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_peak = 148 * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6
+    fp64_ach = KS_FP64_PER_ITEM * B / (avg_ms * 1e-3) if avg_ms else 0.0
     roofline = {
         "bound": "hbm", "kernel": "ks_digits (key-switch digit NTT + key inner product)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -309,7 +317,10 @@ def main():
         "share_of_kernel_time": ks["ms"] / kernel_ms if kernel_ms else None, "dominant_by_time": dom[0],
         "ncu": ({k: ncu[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "lsu_wavefront_pipe_pct", "dram_throughput_pct", "source")}
                 if ncu else None),
-        "note": "exact 64-bit modular arithmetic: bounded by instruction issue / the FP64 and IMAD pipes, not HBM (see DESIGN.md, profiles/)",
+        "note": "exact 64-bit modular arithmetic on the FP64 pipe: bounded by that pipe / the LSU data pipe, not HBM (see DESIGN.md, profiles/)",
+        "fp64_pipe": {"algorithmic_instr_per_item": KS_FP64_PER_ITEM, "achieved_tera_instr_per_s": fp64_ach / 1e12,
+                      "peak_tera_instr_per_s": fp64_peak / 1e12, "frac": fp64_ach / fp64_peak if avg_ms else None,
+                      "peak_source": "148 SMs x 64 FP64 lanes/clk x SM clock sampled during the run (microbench: profiles/r1_pipes_microbench.txt)"},
         "step_level": {"algorithmic_bytes_per_block": BYTES_PER_BLOCK[bool(args.bsgs)],
                        "achieved": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9,
                        "frac": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9 / peak},

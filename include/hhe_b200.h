@@ -107,6 +107,18 @@ int hhe_vec_sum(hhe_ctx *ctx, const uint64_t *a, size_t n, int keyset, uint64_t 
 int hhe_fc_rows(hhe_ctx *ctx, const uint64_t *x, size_t samples, const uint64_t *w, size_t rows, size_t n, int keyset,
                 uint64_t *out);
 
+/* ---- service-level calls (the CSP's request handlers) ---- */
+/* BaseCSP::decompose (src/examples/CSP/CSP.cpp:235-283): per record decomposition (counters restart at 0) -> optional
+ * mask of the last block -> flatten (rotations by -128*i with `flatten_keyset`). out: one ciphertext per record.
+ * apply_mask = 0: the reference service's behaviour (it masks a copy, CSP.cpp:262-269); 1: masks in place like
+ * src/examples/hhe_pktnn_examples.cpp:620-624. Intermediate ciphertexts stay in HBM. */
+int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words, size_t records, uint64_t nonce,
+                      int use_bsgs, int apply_mask, int flatten_keyset, uint64_t *out);
+/* CSP_hhe_pktnn_1fc::evaluateModel (src/examples/CSP/CSP.cpp:288-323): out[records][rows] =
+ * vec_sum(relinearize(record * weight_row), input_len); the dot product lands in slot input_len-1. */
+int hhe_csp_evaluate_model(hhe_ctx *ctx, const uint64_t *records_ct, size_t records, const uint64_t *enc_weights, size_t rows,
+                           size_t input_len, int sum_keyset, uint64_t *out);
+
 /* ---- device-resident variants (inputs/outputs already in HBM; used for kernel-only timing and pipelines) ---- */
 int hhe_dev_alloc(hhe_ctx *ctx, size_t bytes, void **dptr);
 int hhe_dev_free(hhe_ctx *ctx, void *dptr);

@@ -86,7 +86,16 @@ int main(int argc, char **argv) {
   sealhelper_b200::encrypted_vec_sum(g_prod, g_sum, engine, sum_gk, sum_len);
   auto t2 = std::chrono::steady_clock::now();
 
-  bool ok = r_blocks.size() == g_blocks.size();
+  // ---- service-level calls (csp_b200::decompose / evaluate_model = BaseCSP::decompose / evaluateModel in one call each) ----
+  std::vector<Ciphertext> s_flat = csp_b200::decompose(engine, {sym}, enc_key[0], flat_gk);
+  std::vector<std::vector<Ciphertext>> s_res;
+  bool svc_ok = s_flat.size() == 1 && same(s_flat[0], r_flat);
+  if (sum_len == input_len) {  // evaluateModel sums over the whole record
+    s_res = csp_b200::evaluate_model(engine, s_flat, {enc_w}, sum_gk, input_len);
+    svc_ok = svc_ok && s_res.size() == 1 && s_res[0].size() == 1 && same(s_res[0][0], r_sum);
+  }
+
+  bool ok = svc_ok && r_blocks.size() == g_blocks.size();
   for (size_t b = 0; ok && b < r_blocks.size(); b++) ok = same(r_blocks[b], g_blocks[b]);
   ok = ok && same(r_flat, g_flat) && same(r_prod, g_prod) && same(r_sum, g_sum);
   Plaintext p;

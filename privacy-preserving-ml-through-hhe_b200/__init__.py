@@ -26,7 +26,8 @@ SYMBOLS = [
     "hhe_set_batch", "hhe_galois_elt", "hhe_ctx_constants", "hhe_load_ksk", "hhe_has_ksk", "hhe_ntt", "hhe_encode",
     "hhe_add", "hhe_negate", "hhe_add_plain", "hhe_multiply_plain", "hhe_rotate_rows", "hhe_rotate_columns",
     "hhe_multiply", "hhe_square", "hhe_relinearize", "hhe_exponentiate3", "hhe_pasta3_decompose",
-    "hhe_pasta3_decompose_records", "hhe_mask", "hhe_flatten", "hhe_vec_sum", "hhe_fc_rows", "hhe_dev_alloc",
+    "hhe_pasta3_decompose_records", "hhe_mask", "hhe_flatten", "hhe_vec_sum", "hhe_fc_rows", "hhe_csp_decompose",
+    "hhe_csp_evaluate_model", "hhe_dev_alloc",
     "hhe_dev_free", "hhe_dev_upload", "hhe_dev_download", "hhe_sync", "hhe_dev_ntt", "hhe_dev_rotate_rows",
     "hhe_dev_relinearize", "hhe_dev_multiply", "hhe_dev_pasta3_decompose", "hhe_launch_count",
     "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report",
@@ -293,6 +294,25 @@ class Context:
         w, pw, nr = self._cts(w)
         o = np.zeros((ns, nr, 2, self.L, self.N), dtype=np.uint64)
         self._chk(self.lib.hhe_fc_rows(self.h, px, C.c_size_t(ns), pw, C.c_size_t(nr), C.c_size_t(n), keys, o.ctypes.data_as(_u64p)))
+        return o
+
+    # -- service-level calls (BaseCSP::decompose / CSP_hhe_pktnn_1fc::evaluateModel, src/examples/CSP/CSP.cpp:235-323) --------
+    def csp_decompose(self, enc_key, sym_ct, records=1, use_bsgs=False, apply_mask=False, flatten_keys=KEYSET_1, nonce=123456789):
+        k, pk, _ = self._cts(enc_key)
+        s = np.ascontiguousarray(sym_ct, dtype=np.uint64)
+        n_words = s.size // records
+        o = np.zeros((records, 2, self.L, self.N), dtype=np.uint64)
+        self._chk(self.lib.hhe_csp_decompose(self.h, pk, s.ctypes.data_as(_u64p), C.c_size_t(n_words), C.c_size_t(records),
+                                             C.c_uint64(nonce), int(use_bsgs), int(apply_mask), int(flatten_keys),
+                                             o.ctypes.data_as(_u64p)))
+        return o
+
+    def csp_evaluate_model(self, records_ct, enc_weights, input_len, keys=KEYSET_1):
+        x, px, ns = self._cts(records_ct)
+        w, pw, nr = self._cts(enc_weights)
+        o = np.zeros((ns, nr, 2, self.L, self.N), dtype=np.uint64)
+        self._chk(self.lib.hhe_csp_evaluate_model(self.h, px, C.c_size_t(ns), pw, C.c_size_t(nr), C.c_size_t(input_len), keys,
+                                                  o.ctypes.data_as(_u64p)))
         return o
 
     def pasta_layer_material(self, nonce, counter, layer):

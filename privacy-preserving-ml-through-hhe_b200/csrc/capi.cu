@@ -354,6 +354,60 @@ int hhe_pasta3_decompose_records(hhe_ctx *ctx, const uint64_t *enc_key, const ui
   return guarded([&] { decompose_host(E(ctx), enc_key, sym_ct, n_words, records, nonce, first_counter, use_bsgs, out); });
 }
 
+// BaseCSP::decompose (src/examples/CSP/CSP.cpp:235-283) as one call: every record is transciphered (counters restart per
+// record), the last block is optionally masked, and the record's blocks are flattened into one ciphertext. The
+// intermediate ciphertexts never leave HBM. apply_mask = 0 reproduces the reference service (its mask is applied to a
+// copy, CSP.cpp:262-269, so it has no effect); apply_mask = 1 masks in place like the monolithic demo
+// (src/examples/hhe_pktnn_examples.cpp:620-624).
+int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words, size_t records, uint64_t nonce,
+                      int use_bsgs, int apply_mask, int flatten_keyset, uint64_t *out) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    const Params &p = e.params();
+    if (!enc_key || !sym_ct || !out) throw std::invalid_argument("null buffer");
+    if (n_words == 0 || records == 0) return;
+    for (size_t i = 0; i < n_words * records; ++i)
+      if (sym_ct[i] >= p.t) throw std::invalid_argument("input value is larger than plain_modulus");
+    const size_t bpr = (n_words + kPastaT - 1) / kPastaT, rem = n_words % kPastaT, ctw = e.ct_words();
+    Engine::Scope sc(e);
+    u64 *d_key = up(e, enc_key, ctw);
+    u64 *d_ones = nullptr;
+    if (apply_mask && rem) {
+      std::vector<u64> ones(rem, 1);
+      d_ones = up(e, ones.data(), rem);
+    }
+    // chunk over whole records so a chunk's blocks can be flattened on the device
+    const size_t rec_per_chunk = std::max<size_t>(1, static_cast<size_t>(e.batch_limit()) / bpr);
+    for (size_t r0 = 0; r0 < records; r0 += rec_per_chunk) {
+      const size_t nr = std::min(rec_per_chunk, records - r0), nb = nr * bpr;
+      Engine::Scope inner(e);
+      std::vector<u64> sym(nb * kPastaT, 0), ctr(nb);
+      std::vector<u32> lens(nb);
+      for (size_t r = 0; r < nr; ++r)
+        for (size_t b = 0; b < bpr; ++b) {
+          const size_t cnt = std::min<size_t>(kPastaT, n_words - b * kPastaT), blk = r * bpr + b;
+          std::memcpy(&sym[blk * kPastaT], sym_ct + (r0 + r) * n_words + b * kPastaT, cnt * 8);
+          lens[blk] = static_cast<u32>(cnt);
+          ctr[blk] = b;
+        }
+      u64 *d_sym = up(e, sym.data(), nb * kPastaT);
+      u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nb + 1) / 2));
+      e.dev().h2d(d_lens, lens.data(), nb * 4);
+      u64 *d_blocks = e.scratch(nb * ctw), *d_flat = e.scratch(nr * ctw);
+      e.pasta_decompose(d_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_blocks);
+      if (d_ones) {  // mask the last block of every record in place
+        u64 *last = e.scratch(nr * ctw), *masked = e.scratch(nr * ctw);
+        e.strided_copy(d_blocks + (bpr - 1) * ctw, bpr * ctw, last, ctw, ctw, nr);
+        e.mask(last, d_ones, static_cast<u32>(rem), masked, nr);
+        e.strided_copy(masked, ctw, d_blocks + (bpr - 1) * ctw, bpr * ctw, ctw, nr);
+      }
+      e.flatten(d_blocks, bpr, flatten_keyset, d_flat, nr);
+      down(e, out + r0 * ctw, d_flat, nr * ctw);
+      e.dev().sync();
+    }
+  });
+}
+
 int hhe_mask(hhe_ctx *ctx, const uint64_t *a, const uint64_t *mask, size_t n_mask, uint64_t *out, size_t count) {
   return guarded([&] {
     Engine &e = E(ctx);
@@ -425,6 +479,13 @@ int hhe_fc_rows(hhe_ctx *ctx, const uint64_t *x, size_t samples, const uint64_t 
       e.dev().sync();
     }
   });
+}
+
+// CSP_hhe_pktnn_1fc::evaluateModel (src/examples/CSP/CSP.cpp:288-323): every processed record is multiplied with every
+// encrypted weight row, relinearised and summed (packed_enc_multiply -> relinearize_inplace -> encrypted_vec_sum).
+int hhe_csp_evaluate_model(hhe_ctx *ctx, const uint64_t *records_ct, size_t records, const uint64_t *enc_weights, size_t rows,
+                           size_t input_len, int sum_keyset, uint64_t *out) {
+  return hhe_fc_rows(ctx, records_ct, records, enc_weights, rows, input_len, sum_keyset, out);
 }
 
 // ---------------------------------------------------------------------------------------------- device-resident API

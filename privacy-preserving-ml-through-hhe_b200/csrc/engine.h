@@ -72,6 +72,7 @@ class Engine {
   void mask(const u64 *a, const u64 *d_mask_slots, u32 n, u64 *out, size_t items);
   void flatten(const u64 *in, size_t per, int keyset, u64 *out, size_t items);
   void vec_sum(const u64 *a, size_t n, int keyset, u64 *out, size_t items);
+  void strided_copy(const u64 *src, size_t sstride, u64 *dst, size_t dstride, size_t words, size_t rows);
 
   const DevConsts *dconsts() const { return dC_; }
   TwRef twref() const { return TwRef{dTw_, P_.N, f64_gmin_}; }
@@ -84,7 +85,6 @@ class Engine {
                    bool use_bsgs, u64 *d_out);
   void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb);
   void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb);
-  void strided_copy(const u64 *src, size_t sstride, u64 *dst, size_t dstride, size_t words, size_t rows);
   const u32 *ntt_perm(u32 elt);
   void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb);
   void feistel(u64 *state, size_t nb);

@@ -188,3 +188,57 @@ inline void encrypted_vec_sum(const seal::Ciphertext &encrypted_inp, seal::Ciphe
 }
 
 }  // namespace sealhelper_b200
+
+// Service-level mirrors of the CSP request handlers (src/examples/CSP/CSP.cpp): one engine call per request, the
+// intermediate ciphertexts stay in HBM. The keys are uploaded once per analyst (Engine::load), not per call as the
+// reference's per-call PASTA_SEAL construction does (CSP.cpp:238-242).
+namespace csp_b200 {
+
+// BaseCSP::decompose (CSP.cpp:235-283): records -> one flattened ciphertext per record. `apply_mask` = false keeps the
+// reference service's behaviour (its mask acts on a copy, CSP.cpp:262-269).
+inline std::vector<seal::Ciphertext> decompose(hhe_shim::Engine &engine, const std::vector<std::vector<uint64_t>> &records,
+                                               const seal::Ciphertext &enc_sym_key, const seal::GaloisKeys &csp_gk, bool use_bsgs = false,
+                                               bool apply_mask = false) {
+  if (records.empty()) return {};
+  engine.require_fresh_level(enc_sym_key, 2);
+  const size_t n = records[0].size();
+  std::vector<uint64_t> flat_in(records.size() * n), out(records.size() * engine.ct_words());
+  for (size_t r = 0; r < records.size(); ++r) {
+    if (records[r].size() != n) throw std::invalid_argument("records must have equal length");
+    std::memcpy(flat_in.data() + r * n, records[r].data(), sizeof(uint64_t) * n);
+  }
+  if (n > 128) engine.load(csp_gk, HHE_KEYSET_1);
+  hhe_shim::check(hhe_csp_decompose(engine.ctx(), enc_sym_key.data(), flat_in.data(), n, records.size(), 123456789ULL, use_bsgs ? 1 : 0,
+                                    apply_mask ? 1 : 0, HHE_KEYSET_1, out.data()));
+  std::vector<seal::Ciphertext> res;
+  for (size_t r = 0; r < records.size(); ++r) res.push_back(engine.wrap(out.data() + r * engine.ct_words()));
+  return res;
+}
+
+// CSP_hhe_pktnn_1fc::evaluateModel (CSP.cpp:288-323): result[record][row]
+inline std::vector<std::vector<seal::Ciphertext>> evaluate_model(hhe_shim::Engine &engine, const std::vector<seal::Ciphertext> &records,
+                                                                 const std::vector<seal::Ciphertext> &enc_weights,
+                                                                 const seal::GaloisKeys &analyst_gk, size_t input_len) {
+  const size_t ctw = engine.ct_words();
+  std::vector<uint64_t> x(records.size() * ctw), w(enc_weights.size() * ctw), out(records.size() * enc_weights.size() * ctw);
+  for (size_t i = 0; i < records.size(); ++i) {
+    engine.require_fresh_level(records[i], 2);
+    std::memcpy(x.data() + i * ctw, records[i].data(), sizeof(uint64_t) * ctw);
+  }
+  for (size_t i = 0; i < enc_weights.size(); ++i) {
+    engine.require_fresh_level(enc_weights[i], 2);
+    std::memcpy(w.data() + i * ctw, enc_weights[i].data(), sizeof(uint64_t) * ctw);
+  }
+  if (sealhelper_b200::loaded_keys(engine) != &analyst_gk) {
+    engine.load(analyst_gk, HHE_KEYSET_1);
+    sealhelper_b200::loaded_keys(engine) = &analyst_gk;
+  }
+  hhe_shim::check(hhe_csp_evaluate_model(engine.ctx(), x.data(), records.size(), w.data(), enc_weights.size(), input_len, HHE_KEYSET_1,
+                                         out.data()));
+  std::vector<std::vector<seal::Ciphertext>> res(records.size());
+  for (size_t r = 0; r < records.size(); ++r)
+    for (size_t k = 0; k < enc_weights.size(); ++k) res[r].push_back(engine.wrap(out.data() + (r * enc_weights.size() + k) * ctw));
+  return res;
+}
+
+}  // namespace csp_b200

@@ -212,6 +212,35 @@ def test_vec_sum_mask_flatten_fc(eng, world):
             assert np.array_equal(fc[s, r], want)
 
 
+def test_csp_service_calls(eng, world):
+    """hhe_csp_decompose / hhe_csp_evaluate_model against the reference's call sequence (src/examples/CSP/CSP.cpp:235-323):
+    per record decomposition -> (mask of the ragged last block) -> flatten, then multiply -> relinearize -> vec_sum."""
+    o, keys, cts = world["orc"], world["keys"], world["cts"]
+    for s in (-128, -256):
+        elt = o.galois_elt(s)
+        k = keys.galois_key(elt)
+        o.load_ksk(1, elt, k)
+        eng.load_ksk(1, elt, k)
+    rng = np.random.default_rng(21)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    ek = keys.encrypt_zero_plus(o, o.encode(common.pack_key(key, N)))
+    syms = [O.pasta_plain(key, common.T, rng.integers(0, 32, 300, dtype=np.uint64)) for _ in range(2)]  # 3 blocks, 44-word tail
+    ones = np.ones(44, dtype=np.uint64)
+    flat = None
+    for apply_mask in (False, True):
+        got = eng.csp_decompose(ek, np.concatenate(syms), records=2, apply_mask=apply_mask, flatten_keys=1)
+        for r in range(2):
+            blocks = o.pasta_decompose(ek, syms[r])
+            if apply_mask:
+                blocks[-1] = o.mask(blocks[-1], ones)
+            assert np.array_equal(got[r], o.flatten(blocks, 1)), (apply_mask, r)
+        flat = got
+    res = eng.csp_evaluate_model(flat, cts[1:3], 24, 1)
+    for r in range(2):
+        for w in range(2):
+            assert np.array_equal(res[r, w], o.vec_sum(o.relinearize(o.multiply(flat[r], cts[1 + w])), 24, 1))
+
+
 def test_round_material(eng):
     for ctr, layer in ((0, 0), (0, 3), (5, 1), (2**40 + 3, 2)):
         got = eng.pasta_layer_material(common.NONCE, ctr, layer)
