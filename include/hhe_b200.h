@@ -74,6 +74,9 @@ int hhe_ctx_constants(const hhe_ctx *ctx, uint64_t *out);
 
 int hhe_load_ksk(hhe_ctx *ctx, int kind, uint32_t galois_elt, const uint64_t *ksk);
 int hhe_has_ksk(const hhe_ctx *ctx, int kind, uint32_t galois_elt);
+/* Drops every key of one kind: a different seal::GaloisKeys object replaces the previous one as a whole, so a rotation
+ * whose key the new object lacks fails with HHE_ERR_INVALID ("Galois key not present") as it does in SEAL. */
+int hhe_clear_keyset(hhe_ctx *ctx, int kind);
 
 /* ---- SEAL-level primitives, batched over `count` ciphertexts ---- */
 int hhe_ntt(hhe_ctx *ctx, int limb, int inverse, uint64_t *data, size_t count); /* limb<K: q_limb; >=K: Bsk[limb-K] */
@@ -118,6 +121,41 @@ int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym
  * vec_sum(relinearize(record * weight_row), input_len); the dot product lands in slot input_len-1. */
 int hhe_csp_evaluate_model(hhe_ctx *ctx, const uint64_t *records_ct, size_t records, const uint64_t *enc_weights, size_t rows,
                            size_t input_len, int sum_keyset, uint64_t *out);
+
+/* ---- SEAL 4.0 wire format at the boundary ----
+ * The reference moves ciphertexts and keys as seal::Ciphertext / GaloisKeys / RelinKeys ::save byte streams: gRPC payloads
+ * (src/examples/CSP/CSP.cpp:131,201; src/examples/Analyst/Analyst.cpp:258-341; src/examples/User/User.cpp:83,168) and the
+ * decomposition checkpoint file (CSP.cpp:495-547,575-595: size_t count, then `count` saved ciphertexts). These entry points
+ * read/write that format (libs/seal/include/SEAL-4.0/seal/serialization.h:49-91; ciphertext.h:466-642; kswitchkeys.h:186-300)
+ * straight from/to the engine's buffers. Host-side byte work: the stateless ones need no device.
+ * compr_mode: 0 none, 1 zlib, 2 zstd (SEAL's default). Errors: HHE_ERR_LOGIC for invalid data (SEAL: std::logic_error),
+ * HHE_ERR_INVALID for bad arguments, HHE_ERR_RUNTIME when libzstd.so.1 is missing for mode 2. */
+typedef struct hhe_seal_ring {
+  uint64_t N, t;
+  const uint64_t *q; /* key-level primes, last = special prime */
+  int nq;
+} hhe_seal_ring;
+/* EncryptionParameters::parms_id(): level 0 = SEALContext::first_parms_id(), 1 = key_parms_id() */
+int hhe_seal_parms_id(const hhe_seal_ring *ring, int level, uint64_t out[4]);
+size_t hhe_seal_ct_save_bound(const hhe_seal_ring *ring, int size);
+/* Ciphertext::save: ct = u64[size][L][N] (coefficient form, first_parms_id) -> bytes */
+int hhe_seal_ct_save(const hhe_seal_ring *ring, const uint64_t *ct, int size, int compr_mode, uint8_t *out, size_t cap,
+                     size_t *written);
+/* Ciphertext::load(context, ...): validates like SEAL (header, parms_id, dimensions, residues < q_i) */
+int hhe_seal_ct_load(const hhe_seal_ring *ring, const uint8_t *in, size_t len, uint64_t *ct, size_t cap_words, int *size,
+                     size_t *consumed);
+/* GaloisKeys / RelinKeys::load: unpacks every key present into ksk[n][L][2][K][N] (the hhe_load_ksk layout) and its index
+ * ((galois_elt - 1) / 2; 0 for the relinearisation key). ksk == NULL only counts. */
+int hhe_seal_keys_unpack(const hhe_seal_ring *ring, const uint8_t *in, size_t len, uint64_t *index, uint64_t *ksk, size_t cap_keys,
+                         size_t *n_keys, size_t *consumed);
+/* Same walk, every key uploaded to the device as it is parsed: kind = HHE_KEYSET_0/1 for a GaloisKeys stream, HHE_RELIN for
+ * a RelinKeys stream (replaces the by-value key copies of the PASTA_SEAL ctor, CSP.cpp:238-242). */
+int hhe_load_seal_keys(hhe_ctx *ctx, int kind, const uint8_t *in, size_t len, size_t *n_keys, size_t *consumed);
+/* hhe_pasta3_decompose with the serialized forms on both sides: enc_key_bytes = User.cpp:168 payload, out = `nblocks`
+ * Ciphertext::save objects back to back (sizes in out_sizes[nblocks]); what BaseCSP::decompose + the gRPC reply do. */
+int hhe_pasta3_decompose_serialized(hhe_ctx *ctx, const uint8_t *enc_key_bytes, size_t enc_key_len, const uint64_t *sym_ct,
+                                    size_t n_words, uint64_t nonce, uint64_t first_counter, int use_bsgs, int compr_mode, uint8_t *out,
+                                    size_t cap, size_t *out_sizes, size_t *written);
 
 /* ---- device-resident variants (inputs/outputs already in HBM; used for kernel-only timing and pipelines) ---- */
 int hhe_dev_alloc(hhe_ctx *ctx, size_t bytes, void **dptr);

@@ -541,4 +541,64 @@ double ref_bench_primitive(void *h, const uint64_t *ct, int op, int reps) {
   }
 }
 
+// ---- SEAL wire format (Ciphertext/GaloisKeys/RelinKeys::save/load, serialization.h:49-91): checker for the codec ----
+// level 0 = first (data) parms_id, 1 = key parms_id
+void ref_parms_id(void *h, int level, uint64_t *out4) {
+  Ref *r = static_cast<Ref *>(h);
+  const parms_id_type &id = level ? r->ctx->key_parms_id() : r->ctx->first_parms_id();
+  for (size_t i = 0; i < 4; i++) out4[i] = id[i];
+}
+
+// compr: 0 none, 1 zlib, 2 zstd. Returns bytes written (<= cap) or -1.
+long long ref_ct_save(void *h, const uint64_t *ct, int size, int compr, uint8_t *out, size_t cap) {
+  Ref *r = static_cast<Ref *>(h);
+  long long n = -1;
+  guarded([&] {
+    Ciphertext c = make_ct(r, ct, size);
+    n = static_cast<long long>(c.save(reinterpret_cast<seal_byte *>(out), cap, static_cast<compr_mode_type>(compr)));
+  });
+  return n;
+}
+
+// Ciphertext::load(context, bytes): returns bytes consumed or -1; *size_out = ciphertext size, ct_out [size][L][N]
+long long ref_ct_load(void *h, const uint8_t *in, size_t len, uint64_t *ct_out, int *size_out) {
+  Ref *r = static_cast<Ref *>(h);
+  long long n = -1;
+  guarded([&] {
+    Ciphertext c;
+    n = static_cast<long long>(c.load(*r->ctx, reinterpret_cast<const seal_byte *>(in), len));
+    *size_out = static_cast<int>(c.size());
+    dump_ct(r, c, ct_out);
+  });
+  return n;
+}
+
+// kind 0/1: GaloisKeys keyset, 2: RelinKeys. out == NULL: returns the upper bound save_size(compr).
+long long ref_keys_save(void *h, int kind, int compr, uint8_t *out, size_t cap) {
+  Ref *r = static_cast<Ref *>(h);
+  long long n = -1;
+  guarded([&] {
+    const compr_mode_type cm = static_cast<compr_mode_type>(compr);
+    const KSwitchKeys &k = kind == 2 ? static_cast<const KSwitchKeys &>(r->rk) : static_cast<const KSwitchKeys &>(keyset(r, kind));
+    if (!out)
+      n = static_cast<long long>(k.save_size(cm));
+    else
+      n = static_cast<long long>(k.save(reinterpret_cast<seal_byte *>(out), cap, cm));
+  });
+  return n;
+}
+
+// GaloisKeys::load(context, bytes) round trip check: loads, then returns the number of keys present (or -1)
+int ref_galois_load_count(void *h, const uint8_t *in, size_t len) {
+  Ref *r = static_cast<Ref *>(h);
+  int n = -1;
+  guarded([&] {
+    GaloisKeys g;
+    g.load(*r->ctx, reinterpret_cast<const seal_byte *>(in), len);
+    n = 0;
+    for (auto &v : g.data()) n += !v.empty();
+  });
+  return n;
+}
+
 }  // extern "C"

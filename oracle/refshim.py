@@ -37,6 +37,8 @@ def lib():
         l.ref_galois_elt.restype = C.c_uint32
         l.ref_bench_decompose.restype = C.c_double
         l.ref_bench_primitive.restype = C.c_double
+        for f in ("ref_ct_save", "ref_ct_load", "ref_keys_save"):
+            getattr(l, f).restype = C.c_longlong
         _lib = l
     return _lib
 
@@ -103,6 +105,47 @@ class Ref:
         out = np.zeros((self.K, self.N), dtype=np.uint64)
         lib().ref_secret_key(self.h, _p(out))
         return out
+
+    # ---- SEAL wire format (checker for the codec) --------------------------------------------
+    def parms_id(self, level=0):
+        out = np.zeros(4, dtype=np.uint64)
+        lib().ref_parms_id(self.h, level, _p(out))
+        return out
+
+    def ct_save(self, ct, compr=2):
+        c = np.ascontiguousarray(ct, dtype=np.uint64)
+        size = c.size // (self.L * self.N)
+        buf = np.zeros(c.nbytes + 4096, dtype=np.uint8)
+        n = lib().ref_ct_save(self.h, _p(c), size, compr, buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size))
+        if n < 0:
+            raise RefError(lib().ref_last_error().decode())
+        return buf[:n].tobytes()
+
+    def ct_load(self, data):
+        b = np.frombuffer(data, dtype=np.uint8)
+        out = np.zeros((3, self.L, self.N), dtype=np.uint64)
+        size = C.c_int(0)
+        n = lib().ref_ct_load(self.h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size), _p(out), C.byref(size))
+        if n < 0:
+            raise RefError(lib().ref_last_error().decode())
+        return out[: size.value].copy(), int(n)
+
+    def keys_save(self, kind, compr=2):
+        cap = lib().ref_keys_save(self.h, kind, compr, None, C.c_size_t(0))
+        if cap < 0:
+            raise RefError(lib().ref_last_error().decode())
+        buf = np.zeros(cap, dtype=np.uint8)
+        n = lib().ref_keys_save(self.h, kind, compr, buf.ctypes.data_as(C.c_void_p), C.c_size_t(cap))
+        if n < 0:
+            raise RefError(lib().ref_last_error().decode())
+        return buf[:n].tobytes()
+
+    def galois_load_count(self, data):
+        b = np.frombuffer(data, dtype=np.uint8)
+        n = lib().ref_galois_load_count(self.h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size))
+        if n < 0:
+            raise RefError(lib().ref_last_error().decode())
+        return n
 
     # ---- client side -----------------------------------------------------------------------
     def encode(self, slots):

@@ -30,7 +30,9 @@ SYMBOLS = [
     "hhe_csp_evaluate_model", "hhe_dev_alloc",
     "hhe_dev_free", "hhe_dev_upload", "hhe_dev_download", "hhe_sync", "hhe_dev_ntt", "hhe_dev_rotate_rows",
     "hhe_dev_relinearize", "hhe_dev_multiply", "hhe_dev_pasta3_decompose", "hhe_launch_count",
-    "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report",
+    "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report", "hhe_clear_keyset",
+    "hhe_seal_parms_id", "hhe_seal_ct_save_bound", "hhe_seal_ct_save", "hhe_seal_ct_load", "hhe_seal_keys_unpack",
+    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized",
 ]
 
 
@@ -75,6 +77,9 @@ def load_library(path=None):
     l.hhe_launch_count.restype = C.c_uint64
     l.hhe_launch_count.argtypes = [C.c_void_p]
     l.hhe_has_ksk.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    l.hhe_clear_keyset.argtypes = [C.c_void_p, C.c_int]
+    l.hhe_seal_ct_save_bound.restype = C.c_size_t
+    l.hhe_load_seal_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _libs[path] = l
     return l
 
@@ -162,6 +167,39 @@ class Context:
 
     def has_ksk(self, kind, elt):
         return bool(self.lib.hhe_has_ksk(self.h, kind, C.c_uint32(elt)))
+
+    def clear_keyset(self, kind):
+        self._chk(self.lib.hhe_clear_keyset(self.h, int(kind)))
+
+    def load_seal_keys(self, kind, data):
+        """GaloisKeys / RelinKeys::load from the serialized bytes (SEAL wire format), every key uploaded as it is parsed.
+        Returns the number of keys loaded."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        n, used = C.c_size_t(0), C.c_size_t(0)
+        self._chk(self.lib.hhe_load_seal_keys(self.h, int(kind), buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size),
+                                              C.byref(n), C.byref(used)))
+        return int(n.value)
+
+    def pasta3_decompose_serialized(self, enc_key_bytes, sym_ct, use_bsgs=False, nonce=123456789, first_counter=0, compr_mode=2):
+        """Serialized enc. key in, list of serialized result ciphertexts out (the CSP's gRPC request/response payloads)."""
+        from . import seal_io
+        kb = np.frombuffer(bytes(enc_key_bytes), dtype=np.uint8)
+        s = np.ascontiguousarray(sym_ct, dtype=np.uint64)
+        nblk = (s.size + 127) // 128
+        ring = seal_io.Ring(self.N, self.t, self.q, lib=self.lib)
+        cap = nblk * ring.ct_save_bound(2)
+        out = np.zeros(cap, dtype=np.uint8)
+        sizes = (C.c_size_t * max(1, nblk))()
+        written = C.c_size_t(0)
+        self._chk(self.lib.hhe_pasta3_decompose_serialized(
+            self.h, kb.ctypes.data_as(C.c_void_p), C.c_size_t(kb.size), s.ctypes.data_as(_u64p), C.c_size_t(s.size), C.c_uint64(nonce),
+            C.c_uint64(first_counter), int(use_bsgs), int(compr_mode), out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), sizes,
+            C.byref(written)))
+        res, o = [], 0
+        for b in range(nblk):
+            res.append(out[o:o + sizes[b]].tobytes())
+            o += sizes[b]
+        return res
 
     def _cts(self, a, size=2):
         a = np.ascontiguousarray(a, dtype=np.uint64)

@@ -8,6 +8,7 @@
 
 #include "../../include/hhe_b200.h"
 #include "engine.h"
+#include "seal_codec.h"
 
 using namespace hhe;
 
@@ -130,6 +131,10 @@ int hhe_load_ksk(hhe_ctx *ctx, int kind, uint32_t galois_elt, const uint64_t *ks
     if (!ksk) throw std::invalid_argument("null key");
     E(ctx).load_ksk(kind, galois_elt, ksk);
   });
+}
+
+int hhe_clear_keyset(hhe_ctx *ctx, int kind) {
+  return guarded([&] { E(ctx).clear_keyset(kind); });
 }
 
 int hhe_has_ksk(const hhe_ctx *ctx, int kind, uint32_t galois_elt) {
@@ -559,6 +564,102 @@ int hhe_pasta_layer_material(hhe_ctx *ctx, uint64_t nonce, uint64_t counter, int
     e.dev().d2h(mat2, d_mat + (static_cast<size_t>(layer) * 2 + 1) * mw, mw * 4);
     e.dev().d2h(rc, d_mat + kMatWords + layer * 2 * kPastaT, 2 * kPastaT * 4);
     e.dev().sync();
+  });
+}
+
+// ---------------------------------------------------------------------------------------------- SEAL wire format
+namespace {
+sealio::Ring ring_of(const hhe_seal_ring *r) {
+  if (!r || !r->q || r->nq < 2) throw std::invalid_argument("null or incomplete hhe_seal_ring");
+  return sealio::Ring{r->N, r->t, std::vector<uint64_t>(r->q, r->q + r->nq)};
+}
+sealio::Ring ring_from_params(const Params &p) { return sealio::Ring{p.N, p.t, std::vector<uint64_t>(p.q.begin(), p.q.end())}; }
+}  // namespace
+
+int hhe_seal_parms_id(const hhe_seal_ring *ring, int level, uint64_t out[4]) {
+  return guarded([&] {
+    if (!out || level < 0 || level > 1) throw std::invalid_argument("level must be 0 (data) or 1 (key)");
+    sealio::parms_id(ring_of(ring), level, out);
+  });
+}
+
+size_t hhe_seal_ct_save_bound(const hhe_seal_ring *ring, int size) {
+  if (!ring || ring->nq < 2 || size < 1) return 0;
+  return sealio::ct_save_bound(sealio::Ring{ring->N, ring->t, std::vector<uint64_t>(static_cast<size_t>(ring->nq), 0)}, size);
+}
+
+int hhe_seal_ct_save(const hhe_seal_ring *ring, const uint64_t *ct, int size, int compr_mode, uint8_t *out, size_t cap,
+                     size_t *written) {
+  return guarded([&] {
+    const size_t n = sealio::ct_save(ring_of(ring), ct, size, compr_mode, out, cap);
+    if (written) *written = n;
+  });
+}
+
+int hhe_seal_ct_load(const hhe_seal_ring *ring, const uint8_t *in, size_t len, uint64_t *ct, size_t cap_words, int *size,
+                     size_t *consumed) {
+  return guarded([&] {
+    const size_t n = sealio::ct_load(ring_of(ring), in, len, ct, cap_words, size);
+    if (consumed) *consumed = n;
+  });
+}
+
+int hhe_seal_keys_unpack(const hhe_seal_ring *ring, const uint8_t *in, size_t len, uint64_t *index, uint64_t *ksk, size_t cap_keys,
+                         size_t *n_keys, size_t *consumed) {
+  return guarded([&] {
+    const sealio::Ring r = ring_of(ring);
+    const size_t per = static_cast<size_t>(r.L()) * 2 * r.K() * r.N;
+    size_t n = 0;
+    const size_t used = sealio::keys_walk(r, in, len, [&](uint64_t idx, const uint64_t *k) {
+      if (ksk) {
+        if (n >= cap_keys) throw std::invalid_argument("key buffer too small");
+        std::memcpy(ksk + n * per, k, per * 8);
+        if (index) index[n] = idx;
+      }
+      ++n;
+    });
+    if (n_keys) *n_keys = n;
+    if (consumed) *consumed = used;
+  });
+}
+
+int hhe_load_seal_keys(hhe_ctx *ctx, int kind, const uint8_t *in, size_t len, size_t *n_keys, size_t *consumed) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (kind < 0 || kind > 2) throw std::invalid_argument("kind must be HHE_KEYSET_0, HHE_KEYSET_1 or HHE_RELIN");
+    size_t n = 0;
+    const size_t used = sealio::keys_walk(ring_from_params(e.params()), in, len, [&](uint64_t idx, const uint64_t *k) {
+      if (kind == 2 && idx != 0) throw std::logic_error("key data is invalid: RelinKeys with more than one key");
+      e.load_ksk(kind, kind == 2 ? 0u : static_cast<u32>(2 * idx + 1), k);
+      ++n;
+    });
+    if (n_keys) *n_keys = n;
+    if (consumed) *consumed = used;
+  });
+}
+
+int hhe_pasta3_decompose_serialized(hhe_ctx *ctx, const uint8_t *enc_key_bytes, size_t enc_key_len, const uint64_t *sym_ct,
+                                    size_t n_words, uint64_t nonce, uint64_t first_counter, int use_bsgs, int compr_mode, uint8_t *out,
+                                    size_t cap, size_t *out_sizes, size_t *written) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    const sealio::Ring r = ring_from_params(e.params());
+    const size_t ctw = e.ct_words();
+    std::vector<u64> key(ctw);
+    int ksize = 0;
+    sealio::ct_load(r, enc_key_bytes, enc_key_len, key.data(), ctw, &ksize);
+    if (ksize != 2) throw std::invalid_argument("encrypted symmetric key must be a size-2 ciphertext");
+    const size_t nblocks = (n_words + kPastaT - 1) / kPastaT;
+    std::vector<u64> cts(nblocks * ctw);
+    const int rc = hhe_pasta3_decompose(ctx, key.data(), sym_ct, n_words, nonce, first_counter, use_bsgs, cts.data());
+    if (rc != HHE_OK) throw std::runtime_error(g_error);
+    size_t o = 0;
+    for (size_t b = 0; b < nblocks; ++b) {
+      const size_t n = sealio::ct_save(r, cts.data() + b * ctw, 2, compr_mode, out + o, cap - o);
+      if (out_sizes) out_sizes[b] = n;
+      o += n;
+    }
+    if (written) *written = o;
   });
 }
 

@@ -190,6 +190,19 @@ void Engine::load_ksk(int kind, u32 elt, const u64 *host_ksk) {
   keys_[key] = dst;
 }
 
+void Engine::clear_keyset(int kind) {
+  if (kind < 0 || kind > 2) throw std::invalid_argument("key kind must be 0, 1 (galois keysets) or 2 (relin)");
+  dev_.sync();  // no kernel may still read the keys
+  for (auto it = keys_.begin(); it != keys_.end();) {
+    if (it->first.first == kind) {
+      dev_.dfree(it->second);
+      it = keys_.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
 const W2 *Engine::find_key(int kind, u32 elt) const {
   auto it = keys_.find(std::make_pair(kind, kind == 2 ? 0u : elt));
   return it == keys_.end() ? nullptr : it->second;

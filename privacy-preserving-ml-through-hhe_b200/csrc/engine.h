@@ -39,6 +39,7 @@ class Engine {
   // ---- keys ----
   void load_ksk(int kind, u32 elt, const u64 *host_ksk);
   const W2 *find_key(int kind, u32 elt) const;
+  void clear_keyset(int kind);  // drops every key of one kind (a new seal::GaloisKeys object replaces the previous one)
 
   // ---- primitives (device pointers) ----
   void ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride = 0,

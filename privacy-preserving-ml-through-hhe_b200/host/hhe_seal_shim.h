@@ -51,7 +51,10 @@ class Engine {
   size_t ct_words(size_t size = 2) const { return size * L_ * N_; }
 
   // seal::KSwitchKeys (GaloisKeys / RelinKeys) -> engine keyset. ksk layout [digit][2][K][N] = back-to-back PublicKeys.
+  // The object replaces whatever the keyset held before (a key it lacks is then missing, as in SEAL).
   void load(const seal::KSwitchKeys &keys, int kind) {
+    check(hhe_clear_keyset(ctx_, kind));
+    loaded_[kind] = &keys;
     const auto &data = keys.data();
     for (size_t index = 0; index < data.size(); ++index) {
       if (data[index].empty()) continue;
@@ -60,6 +63,22 @@ class Engine {
       const uint32_t elt = kind == HHE_RELIN ? 0u : static_cast<uint32_t>(2 * index + 1);  // GaloisKeys::get_index inverse
       check(hhe_load_ksk(ctx_, kind, elt, flat.data()));
     }
+  }
+
+  // Upload only when a different key object is asked for than the one this keyset holds (the 26-key default set is ~0.5 GB
+  // of PCIe traffic). Identity is by address: callers keep their seal::GaloisKeys alive and unmodified, as the reference does.
+  void ensure_loaded(const seal::KSwitchKeys &keys, int kind) {
+    if (loaded_[kind] != &keys) load(keys, kind);
+  }
+
+  // The same keys as they arrive over gRPC (GaloisKeys/RelinKeys::save bytes, src/examples/Analyst/Analyst.cpp:273-318): parsed by
+  // the engine's SEAL wire-format codec and uploaded key by key, without materialising a seal::GaloisKeys on the host.
+  size_t load_serialized(const std::string &bytes, int kind) {
+    check(hhe_clear_keyset(ctx_, kind));
+    loaded_[kind] = nullptr;
+    size_t n = 0;
+    check(hhe_load_seal_keys(ctx_, kind, reinterpret_cast<const uint8_t *>(bytes.data()), bytes.size(), &n, nullptr));
+    return n;
   }
 
   seal::Ciphertext wrap(const uint64_t *words, size_t size = 2) const {
@@ -78,6 +97,7 @@ class Engine {
   const seal::SEALContext &context_;
   hhe_ctx *ctx_ = nullptr;
   size_t N_ = 0, L_ = 0;
+  const seal::KSwitchKeys *loaded_[3] = {nullptr, nullptr, nullptr};
 };
 
 }  // namespace hhe_shim
@@ -130,7 +150,7 @@ class PASTA_SEAL {
   // src/pasta/SEAL_Cipher.cpp:170-181 (the keys passed here go to keyset 1 so the PASTA keys stay loaded)
   void flatten(std::vector<seal::Ciphertext> &in, seal::Ciphertext &out, const seal::GaloisKeys &galois_keys) {
     if (in.empty()) throw std::invalid_argument("flatten: empty input");
-    engine_->load(galois_keys, HHE_KEYSET_1);
+    engine_->ensure_loaded(galois_keys, HHE_KEYSET_1);
     std::vector<uint64_t> flat(in.size() * engine_->ct_words()), res(engine_->ct_words());
     for (size_t i = 0; i < in.size(); ++i) {
       engine_->require_fresh_level(in[i], 2);
@@ -169,19 +189,10 @@ inline void relinearize_inplace(seal::Ciphertext &encrypted, const hhe_shim::Eng
   encrypted = engine.wrap(out.data());
 }
 
-// remembers which GaloisKeys object is currently uploaded as keyset 1 (uploading the 26-key default set costs ~0.5 GB of PCIe)
-inline const seal::GaloisKeys *&loaded_keys(const hhe_shim::Engine &) {
-  static thread_local const seal::GaloisKeys *p = nullptr;
-  return p;
-}
-
 inline void encrypted_vec_sum(const seal::Ciphertext &encrypted_inp, seal::Ciphertext &destination, hhe_shim::Engine &engine,
                               const seal::GaloisKeys &gal_keys, const size_t vec_size) {
   engine.require_fresh_level(encrypted_inp, 2);
-  if (loaded_keys(engine) != &gal_keys) {
-    engine.load(gal_keys, HHE_KEYSET_1);
-    loaded_keys(engine) = &gal_keys;
-  }
+  engine.ensure_loaded(gal_keys, HHE_KEYSET_1);
   std::vector<uint64_t> out(engine.ct_words());
   hhe_shim::check(hhe_vec_sum(engine.ctx(), encrypted_inp.data(), vec_size, HHE_KEYSET_1, out.data(), 1));
   destination = engine.wrap(out.data());
@@ -207,7 +218,7 @@ inline std::vector<seal::Ciphertext> decompose(hhe_shim::Engine &engine, const s
     if (records[r].size() != n) throw std::invalid_argument("records must have equal length");
     std::memcpy(flat_in.data() + r * n, records[r].data(), sizeof(uint64_t) * n);
   }
-  if (n > 128) engine.load(csp_gk, HHE_KEYSET_1);
+  if (n > 128) engine.ensure_loaded(csp_gk, HHE_KEYSET_1);
   hhe_shim::check(hhe_csp_decompose(engine.ctx(), enc_sym_key.data(), flat_in.data(), n, records.size(), 123456789ULL, use_bsgs ? 1 : 0,
                                     apply_mask ? 1 : 0, HHE_KEYSET_1, out.data()));
   std::vector<seal::Ciphertext> res;
@@ -229,10 +240,7 @@ inline std::vector<std::vector<seal::Ciphertext>> evaluate_model(hhe_shim::Engin
     engine.require_fresh_level(enc_weights[i], 2);
     std::memcpy(w.data() + i * ctw, enc_weights[i].data(), sizeof(uint64_t) * ctw);
   }
-  if (sealhelper_b200::loaded_keys(engine) != &analyst_gk) {
-    engine.load(analyst_gk, HHE_KEYSET_1);
-    sealhelper_b200::loaded_keys(engine) = &analyst_gk;
-  }
+  engine.ensure_loaded(analyst_gk, HHE_KEYSET_1);
   hhe_shim::check(hhe_csp_evaluate_model(engine.ctx(), x.data(), records.size(), w.data(), enc_weights.size(), input_len, HHE_KEYSET_1,
                                          out.data()));
   std::vector<std::vector<seal::Ciphertext>> res(records.size());
