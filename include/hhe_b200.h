@@ -178,6 +178,14 @@ int hhe_profile_enable(hhe_ctx *ctx, int on);
 int hhe_profile_reset(hhe_ctx *ctx);
 int hhe_profile_report(hhe_ctx *ctx, char *buf, size_t cap);
 
+/* ---- client side: plain (non-homomorphic) PASTA-3 for bulk data owners ----
+ * pasta::PASTA::encrypt / decrypt (src/pasta/pasta_3_plain.cpp:9-47; keystream :156-171, round functions :198-282):
+ * out[i] = (in[i] + ks) mod t, or in[i] - ks (+ t if negative) for decrypt, exactly as the reference (inputs are not
+ * reduced on decrypt). key256: the 256-word symmetric key. Block b uses SHAKE counter first_counter + b (reference:
+ * nonce 123456789, counters restart at 0 for every call). The modulus is the context's plain modulus t. */
+int hhe_pasta3_plain(hhe_ctx *ctx, const uint64_t *key256, const uint64_t *in, size_t n_words, uint64_t nonce, uint64_t first_counter,
+                     int decrypt, uint64_t *out);
+
 /* ---- plain PASTA-3 material (device SHAKE128 + matrix generation, for parity tests of that kernel) ---- */
 /* mat1[128*128], mat2[128*128], rc[256] as u32 for (nonce, counter, layer 0..3) */
 int hhe_pasta_layer_material(hhe_ctx *ctx, uint64_t nonce, uint64_t counter, int layer, uint32_t *mat1, uint32_t *mat2,

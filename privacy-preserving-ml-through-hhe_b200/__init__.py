@@ -32,7 +32,7 @@ SYMBOLS = [
     "hhe_dev_relinearize", "hhe_dev_multiply", "hhe_dev_pasta3_decompose", "hhe_launch_count",
     "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report", "hhe_clear_keyset",
     "hhe_seal_parms_id", "hhe_seal_ct_save_bound", "hhe_seal_ct_save", "hhe_seal_ct_load", "hhe_seal_keys_unpack",
-    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized",
+    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized", "hhe_pasta3_plain",
 ]
 
 
@@ -167,6 +167,17 @@ class Context:
 
     def has_ksk(self, kind, elt):
         return bool(self.lib.hhe_has_ksk(self.h, kind, C.c_uint32(elt)))
+
+    def pasta3_plain(self, key256, words, decrypt=False, nonce=123456789, first_counter=0):
+        """pasta::PASTA::encrypt / decrypt (src/pasta/pasta_3_plain.cpp:9-47) on the GPU"""
+        k, pk = _arr(key256)
+        if k.size != 256:
+            raise HheInvalidArgument(HHE_ERR_INVALID, "the PASTA-3 key has 256 words")
+        w, pw = _arr(words)
+        o = np.zeros(w.size, dtype=np.uint64)
+        self._chk(self.lib.hhe_pasta3_plain(self.h, pk, pw, C.c_size_t(w.size), C.c_uint64(nonce), C.c_uint64(first_counter),
+                                            int(decrypt), o.ctypes.data_as(_u64p)))
+        return o
 
     def clear_keyset(self, kind):
         self._chk(self.lib.hhe_clear_keyset(self.h, int(kind)))

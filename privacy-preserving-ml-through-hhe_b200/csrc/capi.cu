@@ -550,6 +550,20 @@ int hhe_dev_pasta3_decompose(hhe_ctx *ctx, const uint64_t *d_enc_key, const uint
   });
 }
 
+int hhe_pasta3_plain(hhe_ctx *ctx, const uint64_t *key256, const uint64_t *in, size_t n_words, uint64_t nonce, uint64_t first_counter,
+                     int decrypt, uint64_t *out) {
+  return guarded([&] {
+    Engine &e = E(ctx);
+    if (!key256 || (!in && n_words) || (!out && n_words)) throw std::invalid_argument("null buffer");
+    if (!n_words) return;
+    Engine::Scope sc(e);
+    u64 *dk = up(e, key256, 2 * kPastaT), *din = up(e, in, n_words), *dout = e.scratch(n_words);
+    e.pasta_plain(dk, din, n_words, nonce, first_counter, decrypt != 0, dout);
+    down(e, out, dout, n_words);
+    e.dev().sync();
+  });
+}
+
 int hhe_pasta_layer_material(hhe_ctx *ctx, uint64_t nonce, uint64_t counter, int layer, uint32_t *mat1, uint32_t *mat2,
                              uint32_t *rc) {
   return guarded([&] {

@@ -756,6 +756,25 @@ void Engine::pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *
   }
 }
 
+// pasta::PASTA::encrypt / decrypt (src/pasta/pasta_3_plain.cpp:9-47): SHAKE material per block, then the keyed permutation
+void Engine::pasta_plain(const u64 *d_key256, const u64 *d_in, size_t n_words, u64 nonce, u64 first_counter, bool decrypt, u64 *d_out) {
+  const size_t nblocks = (n_words + kPastaT - 1) / kPastaT;
+  const size_t step = 1024;  // 512 KiB of round material per block in flight
+  Scope sc(*this);
+  u64 *d_ctr = scratch(std::min(step, nblocks));
+  u32 *mat = reinterpret_cast<u32 *>(scratch((std::min(step, nblocks) * kMaterialWords + 1) / 2));
+  std::vector<u64> ctr(std::min(step, nblocks));
+  for (size_t off = 0; off < nblocks; off += step) {
+    const size_t nb = std::min(step, nblocks - off);
+    for (size_t b = 0; b < nb; ++b) ctr[b] = first_counter + off + b;
+    dev_.h2d(d_ctr, ctr.data(), nb * 8);
+    dev_.sync();  // ctr is reused by the next chunk
+    material(d_ctr, nb, nonce, mat);
+    PastaPlainBody body{mat, d_key256, d_in, d_out, off * kPastaT, n_words, P_.t, decrypt ? 1 : 0};
+    dev_.launch(body, nb, 256, kPastaPlainSmem);
+  }
+}
+
 // SEALZpCipher::mask (src/pasta/SEAL_Cipher.cpp:161-166)
 void Engine::mask(const u64 *a, const u64 *d_mask_slots, u32 n, u64 *out, size_t items) {
   Scope sc(*this);

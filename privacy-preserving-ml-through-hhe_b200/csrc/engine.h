@@ -70,6 +70,8 @@ class Engine {
   void material(const u64 *d_counters, size_t nblocks, u64 nonce, u32 *d_out);
   void pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const std::vector<u64> &counters,
                        u64 nonce, bool use_bsgs, u64 *d_out);
+  // plain PASTA-3 (PASTA::encrypt / decrypt): n_words words, block b uses counter first_counter + b
+  void pasta_plain(const u64 *d_key256, const u64 *d_in, size_t n_words, u64 nonce, u64 first_counter, bool decrypt, u64 *d_out);
   void mask(const u64 *a, const u64 *d_mask_slots, u32 n, u64 *out, size_t items);
   void flatten(const u64 *in, size_t per, int keyset, u64 *out, size_t items);
   void vec_sum(const u64 *a, size_t n, int keyset, u64 *out, size_t items);

@@ -170,4 +170,88 @@ struct MaterialBody {
 };
 constexpr size_t kMaterialSmem = sizeof(u32) * 2 * kPastaT * 3;
 
+// Plain (non-homomorphic) PASTA-3: Pasta::gen_keystream with its round functions (src/pasta/pasta_3_plain.cpp:156-171,198-282) and
+// the word-wise PASTA::encrypt / decrypt (:9-47) for bulk data owners. One CTA per block, consuming the round material
+// MaterialBody produced for that block's counter; thread tid < 256 owns state word (half = tid >> 7, i = tid & 127).
+struct alignas(16) U32x4 {
+  u32 x, y, z, w;
+};
+struct PastaPlainBody {
+  static constexpr const char *kName = "pasta_plain";
+  const u32 *material;  // [blocks][kMaterialWords]
+  const u64 *key;       // [256] symmetric key words (< p)
+  const u64 *in;        // [n_words] plaintext (encrypt) or ciphertext (decrypt)
+  u64 *out;
+  size_t first_word;    // index of this launch's first word inside in/out
+  size_t n_words;       // total length of in/out
+  u64 p;
+  int decrypt;
+  HD void operator()(int bid, int nt, unsigned char *smem) const {
+    constexpr int T = kPastaT;
+    const u32 *mat = material + static_cast<size_t>(bid) * kMaterialWords;
+    u32 *st = reinterpret_cast<u32 *>(smem), *nw = st + 2 * T;
+    FOR_THREADS(tid, nt) {
+      if (tid < 2 * T) st[tid] = static_cast<u32>(key[tid] % p);
+    }
+    SYNC();
+    for (int layer = 0; layer < 4; ++layer) {
+      FOR_THREADS(tid, nt) {  // affine layer: row i of the half's matrix times the half's state, plus round constant
+        if (tid < 2 * T) {
+          const int half = tid >> 7, i = tid & (T - 1);
+          const u32 *row = mat + (static_cast<size_t>(layer) * 2 + half) * T * T + static_cast<size_t>(i) * T;
+          const u32 *sv = st + half * T;
+          u64 acc = 0;  // 128 products below 2^34 each: no overflow
+          for (int j = 0; j < T; j += 4) {
+            const U32x4 m4 = *reinterpret_cast<const U32x4 *>(row + j);
+            acc += static_cast<u64>(m4.x) * sv[j] + static_cast<u64>(m4.y) * sv[j + 1] + static_cast<u64>(m4.z) * sv[j + 2] +
+                   static_cast<u64>(m4.w) * sv[j + 3];
+          }
+          nw[tid] = static_cast<u32>((acc % p + mat[kMatWords + layer * 2 * T + tid]) % p);
+        }
+      }
+      SYNC();
+      FOR_THREADS(tid, nt) {  // mix: (a, b) -> (2a + b, a + 2b)
+        if (tid < 2 * T) {
+          const int i = tid & (T - 1);
+          const u64 sum = (static_cast<u64>(nw[i]) + nw[T + i]) % p;
+          st[tid] = static_cast<u32>((nw[tid] + sum) % p);
+        }
+      }
+      SYNC();
+      if (layer == 3) break;
+      FOR_THREADS(tid, nt) {  // S-box: Feistel x_i += x_{i-1}^2 (rounds 1, 2), cube (round 3), per half
+        if (tid < 2 * T) {
+          const int i = tid & (T - 1);
+          const u64 v = st[tid];
+          if (layer == 2) {
+            nw[tid] = static_cast<u32>(v * v % p * v % p);
+          } else {
+            const u64 prev = i ? st[tid - 1] : 0;
+            nw[tid] = static_cast<u32>((prev * prev + v) % p);
+          }
+        }
+      }
+      SYNC();
+      FOR_THREADS(tid, nt) {
+        if (tid < 2 * T) st[tid] = nw[tid];
+      }
+      SYNC();
+    }
+    FOR_THREADS(tid, nt) {  // the keystream is the first half of the state
+      const size_t w = first_word + static_cast<size_t>(bid) * T + tid;
+      if (tid < T && w < n_words) {
+        const u64 ks = st[tid];
+        u64 v = in[w];
+        if (decrypt) {
+          if (ks > v) v += p;  // exactly PASTA::decrypt (:39-41): no reduction of the input
+          out[w] = v - ks;
+        } else {
+          out[w] = (v + ks) % p;
+        }
+      }
+    }
+  }
+};
+constexpr size_t kPastaPlainSmem = sizeof(u32) * 4 * kPastaT;
+
 }  // namespace hhe
