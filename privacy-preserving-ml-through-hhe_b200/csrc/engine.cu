@@ -566,10 +566,11 @@ const u64 *Engine::feistel_mask_ntt() {
 }
 
 // PASTA_SEAL::diagonal (src/pasta/pasta_3_seal.cpp:370-413); the 128 products are summed in the NTT domain.
-void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb) {
+void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, bool shared) {
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(P_.L) * N;
-  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nb * N), *D = scratch(nb * dw);
+  const size_t nd = shared ? 1 : nb, ds = shared ? 0 : dw;  // diagonals: one set per block, or one for the whole batch
+  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nd * N), *D = scratch(nd * dw);
   if (N / 2 != kPastaT) {
     rotate_rows(state, kPastaT, 0, tmp, nb);
     add(state, tmp, state, nb);
@@ -582,9 +583,9 @@ void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb) {
       apply_galois(cur, e1, k1, nxt, nb);
       std::swap(cur, nxt);
     }
-    encode_material(mat, nullptr, kDiag, layer, i, pt, nb);
-    lift_ntt(pt, D, nb);
-    ntt_mac(cur, D, dw, sum, nb, i == 0);
+    encode_material(mat, nullptr, kDiag, layer, i, pt, nd);
+    lift_ntt(pt, D, nd);
+    ntt_mac(cur, D, ds, sum, nb, i == 0);
   }
   ntt(sum, state, nb, 2 * P_.L, map_mod(2 * P_.L, P_.L, 0), true);
 }
@@ -592,11 +593,12 @@ void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb) {
 // Same computation with the rotating state kept NTT-resident (see kernels.h "NTT-resident rotation chain"): per
 // rotation 64 + 10 + 8 + 8 limb transforms instead of 72 + 18 + 16. Used when every coefficient prime is on the FP64
 // path; bit-identical to affine_diagonal (tests/test_engine_parity.py compares both rings with the oracle).
-void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb) {
+void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, bool shared) {
   Scope sc(*this);
   const int L = P_.L, K = P_.K;
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(L) * N;
-  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nb * N), *D = scratch(nb * dw);
+  const size_t nd = shared ? 1 : nb, ds = shared ? 0 : dw;
+  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nd * N), *D = scratch(nd * dw);
   u64 *stn = scratch(nb * ctw), *c0a = scratch(nb * dw), *c0b = scratch(nb * dw), *c1c = scratch(nb * dw), *c1n = scratch(nb * dw),
       *g1 = scratch(nb * dw), *acc = scratch(nb * 2 * K * N);
   if (N / 2 != kPastaT) {
@@ -608,9 +610,9 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   const u32 *perm = ntt_perm(e1);
   const u32 e1_inv = inv_mod_2n(e1, 2 * N);
   // step 0: sum = NTT(state) * D_0, keeping NTT(state)
-  encode_material(mat, nullptr, kDiag, layer, 0, pt, nb);
-  lift_ntt(pt, D, nb);
-  ntt_mac(state, D, dw, sum, nb, true, 2, 0, stn);
+  encode_material(mat, nullptr, kDiag, layer, 0, pt, nd);
+  lift_ntt(pt, D, nd);
+  ntt_mac(state, D, ds, sum, nb, true, 2, 0, stn);
   strided_copy(stn, ctw, c0a, dw, dw, nb);
   strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
   strided_copy(state + dw, ctw, c1c, dw, dw, nb);
@@ -639,32 +641,33 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
         dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     }
-    encode_material(mat, nullptr, kDiag, layer, i, pt, nb);
-    lift_ntt(pt, D, nb);
+    encode_material(mat, nullptr, kDiag, layer, i, pt, nd);
+    lift_ntt(pt, D, nd);
     if (half_fwd_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
-        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref()};
+        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds};
         dev_.launch(body, nb * L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     } else {
       HHE_DISPATCH_LOG(P_.logn, {
-        Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref()};
+        Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds};
         dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     }
     std::swap(c0_in, c0_out);
-    ntt_mac(c1c, D, dw, sum, nb, false, 1, dw, c1n);
+    ntt_mac(c1c, D, ds, sum, nb, false, 1, dw, c1n);
   }
   ntt(sum, state, nb, 2 * L, map_mod(2 * L, L, 0), true);
 }
 
 // PASTA_SEAL::babystep_giantstep (src/pasta/pasta_3_seal.cpp:267-366), N1 = 16, N2 = 8
-void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb) {
+void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, bool shared) {
   constexpr int N1 = 16, N2 = 8;
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(P_.L) * N;
-  u64 *tmp = scratch(nb * ctw), *inner = scratch(nb * ctw), *outer = scratch(nb * ctw), *pt = scratch(nb * N),
-      *D = scratch(nb * dw), *rot = scratch(nb * ctw * N1);
+  const size_t nd = shared ? 1 : nb, ds = shared ? 0 : dw;
+  u64 *tmp = scratch(nb * ctw), *inner = scratch(nb * ctw), *outer = scratch(nb * ctw), *pt = scratch(nd * N),
+      *D = scratch(nd * dw), *rot = scratch(nb * ctw * N1);
   if (N / 2 != kPastaT) {
     rotate_rows(state, kPastaT, 0, tmp, nb);
     add(state, tmp, state, nb);
@@ -676,9 +679,9 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb) {
   ntt(rot, rot, nb * N1, 2 * P_.L, mq, false);
   for (int k = 0; k < N2; ++k) {
     for (int j = 0; j < N1; ++j) {
-      encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt, nb);
-      lift_ntt(pt, D, nb);
-      DyadicMacBody mac{rot + j * nb * ctw, D, inner, dC_, j == 0 ? 1 : 0, nb * ctw};
+      encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt, nd);
+      lift_ntt(pt, D, nd);
+      DyadicMacBody mac{rot + j * nb * ctw, D, inner, dC_, j == 0 ? 1 : 0, nb * ctw, ds};
       dev_.launch(mac, ew_grid(nb * ctw), kEwThreads, 0);
     }
     if (k == 0) {
@@ -706,23 +709,26 @@ void Engine::feistel(u64 *state, size_t nb) {
 }
 
 void Engine::pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb,
-                         u64 nonce, bool use_bsgs, u64 *d_out) {
+                         u64 nonce, bool use_bsgs, bool shared, u64 *d_out) {
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N;
+  // `shared`: every block of the batch has the same SHAKE counter (records restart at counter 0), so the
+  // round material, the encoded diagonals and their lifted transforms are computed once and read by all blocks.
+  const size_t nm = shared ? 1 : nb;
   u64 *state = scratch(nb * ctw), *tmp = scratch(nb * ctw), *pt = scratch(nb * N);
-  u32 *mat = reinterpret_cast<u32 *>(scratch((nb * kMaterialWords + 1) / 2));
+  u32 *mat = reinterpret_cast<u32 *>(scratch((nm * kMaterialWords + 1) / 2));
   feistel_mask_ntt();
-  material(d_counters, nb, nonce, mat);
+  material(d_counters, nm, nonce, mat);
   broadcast(d_enc_key, state, ctw, nb);
   for (int layer = 0; layer < 4; ++layer) {
     if (use_bsgs)
-      affine_bsgs(state, mat, layer, nb);
+      affine_bsgs(state, mat, layer, nb, shared);
     else if (compact_keys_ && !getenv_flag("HHE_NO_RESIDENT"))
-      affine_diagonal_resident(state, mat, layer, nb);
+      affine_diagonal_resident(state, mat, layer, nb, shared);
     else
-      affine_diagonal(state, mat, layer, nb);
-    encode_material(mat, nullptr, kRc, layer, 0, pt, nb);  // add_rc (:205-211)
-    add_plain(state, pt, N, state, nb, false);
+      affine_diagonal(state, mat, layer, nb, shared);
+    encode_material(mat, nullptr, kRc, layer, 0, pt, nm);  // add_rc (:205-211)
+    add_plain(state, pt, shared ? 0 : N, state, nb, false);
     rotate_columns(state, 0, tmp, nb);  // mix (:417-423)
     add(tmp, state, tmp, nb);
     add(state, tmp, state, nb);
@@ -752,7 +758,9 @@ void Engine::pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *
   for (size_t off = 0; off < nblocks; off += step) {
     const size_t nb = std::min(step, nblocks - off);
     dev_.h2d(d_ctr, counters.data() + off, nb * 8);
-    pasta_batch(d_enc_key, d_sym + off * kPastaT, d_lens + off, d_ctr, nb, nonce, use_bsgs, d_out + off * ct_words());
+    bool shared = nb > 1 && !getenv_flag("HHE_NO_SHARED_MATERIAL");
+    for (size_t b = 1; b < nb && shared; ++b) shared = counters[off + b] == counters[off];
+    pasta_batch(d_enc_key, d_sym + off * kPastaT, d_lens + off, d_ctr, nb, nonce, use_bsgs, shared, d_out + off * ct_words());
   }
 }
 

@@ -85,11 +85,11 @@ class Engine {
   friend struct Scope;
   void arena_restore(size_t chunk, size_t used);
   void pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb, u64 nonce,
-                   bool use_bsgs, u64 *d_out);
-  void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb);
-  void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb);
+                   bool use_bsgs, bool shared, u64 *d_out);
+  void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, bool shared);
+  void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, bool shared);
   const u32 *ntt_perm(u32 elt);
-  void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb);
+  void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, bool shared);
   void feistel(u64 *state, size_t nb);
   const W2 *need_key(int kind, u32 elt) const;
   void require_whole_limb(const char *what) const;

@@ -1145,11 +1145,12 @@ struct NttMacBody {
 struct DyadicMacBody {
   static constexpr const char *kName = "dyadic_mac";
   const u64 *a;  // [items][2][L][N] NTT form
-  const u64 *D;  // [items][L][N]
+  const u64 *D;  // [items][L][N] (dstride = L*N) or shared by all items (dstride = 0)
   u64 *sum;      // [items][2][L][N]
   const DevConsts *C;
   int first;
   size_t total;  // items * 2 * L * N
+  size_t dstride;
   HD void operator()(int bid, int nt, unsigned char *) const {
     const size_t N = C->N;
     const u32 L = static_cast<u32>(C->L);
@@ -1159,7 +1160,7 @@ struct DyadicMacBody {
         const u32 limb = static_cast<u32>(g >> C->logn);
         const u32 i = limb % L, item = limb / (2 * L);
         const DevMod mi = C->mod[i];
-        u64 v = mul_mod(a[g], D[(static_cast<size_t>(item) * L + i) * N + (g & (N - 1))], mi);
+        u64 v = mul_mod(a[g], D[static_cast<size_t>(item) * dstride + static_cast<size_t>(i) * N + (g & (N - 1))], mi);
         if (!first) v = add_mod(v, sum[g], mi.q);
         sum[g] = v;
       }
@@ -1340,10 +1341,11 @@ struct Corr0MacBody {
   const u64 *c0_in;   // [items][L][N] NTT form
   u64 *c0_out;        // [items][L][N]
   const u32 *perm;    // NTT-slot permutation of the Galois element
-  const u64 *D;       // [items][L][N]
+  const u64 *D;       // [items][L][N], or shared by all items (dstride = 0)
   u64 *sum;           // [items][2][L][N], component 0 updated
   const DevConsts *C;
   TwRef tw;
+  size_t dstride;     // L*N or 0
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     const int L = C->L, K = C->K, i = bid % L;
@@ -1357,7 +1359,7 @@ struct Corr0MacBody {
     const u64 *a0 = acc + ((item * 2) * K + i) * S;
     const u64 *cin = c0_in + (item * L + i) * S;
     u64 *cout = c0_out + (item * L + i) * S;
-    const u64 *d = D + (item * L + i) * S;
+    const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
     u64 *s0 = sum + (item * 2 * L + i) * S;
     FOR_THREADS(tid, nt) {
       constexpr int U = 4;  // independent gathers in flight per thread (perm -> c0 is a dependent pair of loads)
@@ -1483,10 +1485,11 @@ struct Corr0MacHalfBody {
   const u64 *c0_in;   // [items][L][N] NTT form
   u64 *c0_out;        // [items][L][N]
   const u32 *perm;    // NTT-slot permutation of the Galois element
-  const u64 *D;       // [items][L][N]
+  const u64 *D;       // [items][L][N], or shared by all items (dstride = 0)
   u64 *sum;           // [items][2][L][N], component 0 updated
   const DevConsts *C;
   TwRef tw;
+  size_t dstride;     // L*N or 0
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
@@ -1503,7 +1506,7 @@ struct Corr0MacHalfBody {
     const u64 *a0 = acc + ((item * 2) * K + i) * N + hoff;
     const u64 *cin = c0_in + (item * L + i) * N;
     u64 *cout = c0_out + (item * L + i) * N + hoff;
-    const u64 *d = D + (item * L + i) * N + hoff;
+    const u64 *d = D + item * dstride + static_cast<size_t>(i) * N + hoff;
     u64 *s0 = sum + (item * 2 * L + i) * N + hoff;
     const u32 *pm = perm + hoff;
     const D2 isp = C->inv_sp_f[i];

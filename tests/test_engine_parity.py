@@ -266,6 +266,19 @@ def test_transciphering_vs_oracle(eng, world, bsgs):
         assert np.array_equal(eng.pasta3_decompose(ek, sym[128:256], first_counter=1)[0], want[1])
 
 
+@pytest.mark.parametrize("bsgs", [False, True])
+def test_records_sharing_one_counter(eng, world, bsgs):
+    """Records restart at counter 0 (CSP.cpp:247-252): a batch of one-block records shares its round
+    material, diagonals and their transforms. Same ciphertexts as transciphering each record on its own."""
+    o, keys, rng = world["orc"], world["keys"], np.random.default_rng(23)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    ek = keys.encrypt_zero_plus(o, o.encode(common.pack_key(key, N)))
+    recs = [O.pasta_plain(key, common.T, rng.integers(0, common.T, 100, dtype=np.uint64)) for _ in range(3)]
+    got = eng.pasta3_decompose(ek, np.concatenate(recs), use_bsgs=bsgs, records=3)
+    for r in range(3):
+        assert np.array_equal(got[r], o.pasta_decompose(ek, recs[r], use_bsgs=bsgs)[0]), r
+
+
 # ---- golden vectors generated from the reference itself ---------------------------------------------------------------
 @pytest.fixture(scope="module", params=BACKENDS)
 def eng512(request):
@@ -403,4 +416,34 @@ def test_missing_keys_raise(backend):
         ctx.rotate_rows(ct, -1)  # "Galois key not present"
     with pytest.raises(pkg.HheInvalidArgument):
         ctx.pasta3_decompose(ct, np.arange(4, dtype=np.uint64))  # PASTA needs steps -1, +128, columns and relin
+    ctx.close()
+
+
+# ---- client side: plain PASTA-3 on the device ------------------------------------------------
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_plain_pasta3_matches_reference_kat_and_oracle(backend):
+    """pasta::PASTA::encrypt / decrypt (src/pasta/pasta_3_plain.cpp:9-47): SURVEY.md Appendix E KAT (generated by the reference,
+    committed in tests/golden), the oracle on ragged lengths, and the encrypt -> decrypt round trip."""
+    ctx = make_ctx(backend, N, common.small_params(N, 3, 48))
+    key = FX["sym_key"]
+    # KAT: plaintext 0..255 (two blocks) under get_symmetric_key()
+    kat = ctx.pasta3_plain(key, FX["kat_plain"])
+    assert np.array_equal(kat, FX["kat_cipher"])
+    assert list(kat[:8]) == [30446, 62406, 62716, 38766, 43125, 6036, 63532, 7424] and list(kat[128:132]) == [11021, 61753, 2637, 43237]
+    rng = np.random.default_rng(12)
+    for n in (1, 127, 128, 129, 300, 5 * 128 + 17):
+        words = rng.integers(0, common.T, n, dtype=np.uint64)
+        enc = ctx.pasta3_plain(key, words)
+        assert np.array_equal(enc, O.pasta_plain(key, common.T, words, decrypt=False))
+        assert np.array_equal(ctx.pasta3_plain(key, enc, decrypt=True), words)
+    # counters: block b of a long call == block 0 of a call that starts at counter b
+    words = rng.integers(0, common.T, 3 * 128, dtype=np.uint64)
+    whole = ctx.pasta3_plain(key, words)
+    assert np.array_equal(whole[256:], ctx.pasta3_plain(key, words[256:], first_counter=2))
+    # unreduced inputs: encrypt reduces, decrypt does not (pasta_3_plain.cpp:20-23 vs :39-41)
+    odd = np.array([common.T + 5, 2 * common.T, 70000], dtype=np.uint64)
+    assert np.array_equal(ctx.pasta3_plain(key, odd), O.pasta_plain(key, common.T, odd, decrypt=False))
+    assert ctx.pasta3_plain(key, np.zeros(0, dtype=np.uint64)).size == 0
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.pasta3_plain(key[:100], words)
     ctx.close()

@@ -89,6 +89,19 @@ def test_batch_and_counter_invariance(world):
         assert np.array_equal(slots[:n], pt[b * 128:b * 128 + n])
 
 
+def test_records_sharing_counter_zero(world):
+    """BASELINE.json configs[2] shape (ECG: one-block records, every record restarts at counter 0): the batch shares its round
+    material and diagonals; each record's ciphertext equals the one from a call of its own, and block 0 is SEAL's."""
+    ref, ctx, rng, key = world["ref"], world["ctx"], world["rng"], world["key"]
+    pts = rng.integers(0, 256, (5, 128), dtype=np.uint64)
+    syms = np.stack([O.pasta_plain(key, common.T, p) for p in pts])
+    got = ctx.pasta3_decompose(world["enc_key"], syms.reshape(-1), records=5)
+    assert np.array_equal(got[0], ref.pasta_decompose(world["enc_key"], syms[0])[0])
+    for r in (1, 4):
+        assert np.array_equal(got[r], ctx.pasta3_decompose(world["enc_key"], syms[r])[0])
+        assert np.array_equal(ref.decrypt(got[r])[0][:128], pts[r])
+
+
 def test_n32768_primitives_bit_exact_with_seal():
     """BASELINE.json configs[4] (primitive sweep) at N=32768, BFVDefault (L=15 + special): NTT, rotate, relinearize, multiply."""
     NN = 32768
