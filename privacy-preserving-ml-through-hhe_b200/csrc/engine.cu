@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <map>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -753,14 +754,56 @@ void Engine::pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *
   need_key(2, 0);
   if (P_.N / 2 != kPastaT) need_key(0, P_.galois_elt_from_step(kPastaT));
   Scope sc(*this);
-  const size_t step = static_cast<size_t>(std::max(1, batch_));
+  const size_t step = static_cast<size_t>(std::max(1, batch_)), ctw = ct_words();
   u64 *d_ctr = scratch(std::min(step, nblocks));
-  for (size_t off = 0; off < nblocks; off += step) {
-    const size_t nb = std::min(step, nblocks - off);
-    dev_.h2d(d_ctr, counters.data() + off, nb * 8);
-    bool shared = nb > 1 && !getenv_flag("HHE_NO_SHARED_MATERIAL");
-    for (size_t b = 1; b < nb && shared; ++b) shared = counters[off + b] == counters[off];
-    pasta_batch(d_enc_key, d_sym + off * kPastaT, d_lens + off, d_ctr, nb, nonce, use_bsgs, shared, d_out + off * ct_words());
+  // Blocks with equal SHAKE counters (records restart at counter 0: CSP.cpp:247-252) have identical round
+  // matrices and constants. They are regrouped into batches of one counter each, which compute the round material, the encoded
+  // diagonals and their lifted transforms once per batch instead of once per block; the remaining blocks form ordinary batches.
+  std::map<u64, std::vector<u32>> by_counter;
+  if (!getenv_flag("HHE_NO_SHARED_MATERIAL") && nblocks < (static_cast<size_t>(1) << 32))
+    for (size_t b = 0; b < nblocks; ++b) by_counter[counters[b]].push_back(static_cast<u32>(b));
+  if (by_counter.empty() || by_counter.size() == nblocks) {  // all counters distinct: blocks are processed where they lie
+    for (size_t off = 0; off < nblocks; off += step) {
+      const size_t nb = std::min(step, nblocks - off);
+      dev_.h2d(d_ctr, counters.data() + off, nb * 8);
+      pasta_batch(d_enc_key, d_sym + off * kPastaT, d_lens + off, d_ctr, nb, nonce, use_bsgs, false, d_out + off * ctw);
+    }
+    return;
+  }
+  std::vector<u32> singles;
+  std::vector<std::pair<std::vector<u32>, bool>> batches;  // (block indices, shared)
+  for (auto &kv : by_counter) {
+    if (kv.second.size() == 1) {
+      singles.push_back(kv.second[0]);
+      continue;
+    }
+    for (size_t off = 0; off < kv.second.size(); off += step) {
+      const size_t nb = std::min(step, kv.second.size() - off);
+      batches.emplace_back(std::vector<u32>(kv.second.begin() + off, kv.second.begin() + off + nb), nb > 1);
+    }
+  }
+  std::sort(singles.begin(), singles.end());
+  for (size_t off = 0; off < singles.size(); off += step)
+    batches.emplace_back(std::vector<u32>(singles.begin() + off, singles.begin() + std::min(singles.size(), off + step)), false);
+  const size_t cap = std::min(step, nblocks);
+  u32 *d_idx = reinterpret_cast<u32 *>(scratch((cap + 1) / 2)), *g_lens = reinterpret_cast<u32 *>(scratch((cap + 1) / 2));
+  u64 *g_sym = scratch(cap * kPastaT), *g_out = scratch(cap * ctw);
+  std::vector<u64> ctr;
+  for (auto &bt : batches) {
+    const std::vector<u32> &idx = bt.first;
+    const size_t nb = idx.size();
+    ctr.resize(nb);
+    for (size_t i = 0; i < nb; ++i) ctr[i] = counters[idx[i]];
+    dev_.h2d(d_ctr, ctr.data(), nb * 8);
+    dev_.h2d(d_idx, idx.data(), nb * 4);
+    dev_.sync();  // ctr / idx live on the host stack of this loop
+    GatherRowsBody<u64> gs{d_sym, g_sym, d_idx, static_cast<size_t>(kPastaT), nb * kPastaT, 0};
+    dev_.launch(gs, ew_grid(nb * kPastaT), kEwThreads, 0);
+    GatherRowsBody<u32> gl{d_lens, g_lens, d_idx, 1, nb, 0};
+    dev_.launch(gl, ew_grid(nb), kEwThreads, 0);
+    pasta_batch(d_enc_key, g_sym, g_lens, d_ctr, nb, nonce, use_bsgs, bt.second, g_out);
+    GatherRowsBody<u64> so{g_out, d_out, d_idx, ctw, nb * ctw, 1};
+    dev_.launch(so, ew_grid(nb * ctw), kEwThreads, 0);
   }
 }
 

@@ -1305,6 +1305,29 @@ struct StridedCopyBody {
   }
 };
 
+// Row gather / scatter by index (blocks regrouped by SHAKE counter, Engine::pasta_decompose): units of `unit` bytes' worth of T
+template <class T>
+struct GatherRowsBody {
+  static constexpr const char *kName = "gather_rows";
+  const T *src;
+  T *dst;
+  const u32 *idx;  // [rows]
+  size_t words, total;  // total = rows * words
+  int scatter;     // 0: dst[r] = src[idx[r]]   1: dst[idx[r]] = src[r]
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t r = g / words, w = g % words, o = static_cast<size_t>(idx[r]) * words + w;
+        if (scatter)
+          dst[o] = src[g];
+        else
+          dst[g] = src[o];
+      }
+    }
+  }
+};
+
 // ModDown of component 1 only: c1[i][j] = (acc1[i][j] - (r1[j] mod q_i) + half_i) * q_sp^-1, acc1 in coefficient form
 struct ModDownC1Body {
   static constexpr const char *kName = "moddown_c1";
