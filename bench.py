@@ -289,6 +289,30 @@ def main():
         same = np.array_equal(out_host[0].numpy().view(np.uint64), d_out[0].cpu().numpy().view(np.uint64))
         assert same, "host-API and device-API outputs differ"
 
+    # ---- "NTT GB/s" (the second figure BASELINE.json's metric names): forward / inverse negacyclic NTT of every limb of the output batch (621 MB at 296 blocks,
+    # larger than L2) in HBM, 2 x 8N bytes per limb-transform; CUDA events on the engine's stream, rank 0 only ----
+    ntt_info = None
+    if rank == 0:
+        limbs = 2 * L * B
+        d_l = d_out.view(-1)[: limbs * N]
+        rngl = torch.Generator(device="cuda").manual_seed(7)
+        d_l.copy_(torch.randint(0, int(common.Q_16384[0]), (limbs * N,), dtype=torch.int64, device="cuda", generator=rngl))
+        torch.cuda.synchronize()
+        res = {}
+        for name, inv in (("fwd", False), ("inv", True)):
+            for _ in range(3):
+                ctx.dev_ntt(0, inv, ptr(d_l), limbs)
+            ctx.sync()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record(stream)
+            for _ in range(10):
+                ctx.dev_ntt(0, inv, ptr(d_l), limbs)
+            n1.record(stream)
+            ctx.sync()
+            t = n0.elapsed_time(n1) / 10
+            res[name] = {"GBps": limbs * 16 * N / t / 1e6, "limb_transforms_per_s": limbs / t * 1e3, "frac_of_hbm_peak": limbs * 16 * N / t / 1e6 / peak_hbm()[0]}
+        ntt_info = {"limbs_per_launch": limbs, "bytes_per_limb": 16 * N, "fwd": res["fwd"], "inv": res["inv"],
+                    "note": "exact 49-bit modular transforms on the FP64 pipe (7 FP64 + 1 FRND per butterfly): pipe ceiling = 23 M limbs/s = 6.1 TB/s equivalent"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -343,7 +367,7 @@ def main():
         "data": "synthetic", "config": config(args, world), "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ek_host.numel() * 8 + sym_host.numel() * 8 + B * 12),
                 "d2h_bytes_per_step": int(out_host.numel() * 8)},
-        "gpu_launches": int(launches), "clocks": clocks, "verified": checked,
+        "gpu_launches": int(launches), "clocks": clocks, "verified": checked, "ntt": ntt_info,
     }
     print(json.dumps(out))
 

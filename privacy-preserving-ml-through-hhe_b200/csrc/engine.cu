@@ -240,10 +240,18 @@ void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap 
     }
     return;
   }
-  if (inverse && cluster_inv_) {
+  if (cluster_inv_) {
     bool all_f64 = true;
     for (int l = 0; l < limbs; ++l) all_f64 = all_f64 && table_is_f64(P_, map.id[l]);
-    if (all_f64) {
+    if (all_f64 && !inverse && !getenv_flag("HHE_NO_FWD_CLUSTER")) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        NttFwdClusterBody<LOGV> body{in, out, dC_, twref(), map, limbs, item_stride ? item_stride : static_cast<size_t>(limbs) << (LOGV + 1),
+                                     limb_stride ? limb_stride : static_cast<size_t>(2) << LOGV};
+        dev_.launch_cluster2(body, items * limbs * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+      return;
+    }
+    if (all_f64 && inverse) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
         using Body = InvClusterBody<LOGV, PlanScaled>;
         Body body{PlanScaled{in, out, map, limbs, item_stride ? item_stride : static_cast<size_t>(limbs) << (LOGV + 1),

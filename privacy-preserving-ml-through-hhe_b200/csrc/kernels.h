@@ -1723,6 +1723,42 @@ struct InvClusterBody {
   }
 };
 
+// Forward counterpart for whole-limb transforms (FP64 path): the pair of half-limb CTAs of a limb forms a two-CTA cluster. Each
+// folds the first Cooley-Tukey stage into its load (reading the whole limb), the cluster barrier separates all reads of the limb
+// from the first store, so the transform may run in place; the passes and the store then touch only the CTA's own half.
+template <int LOGH>
+struct NttFwdClusterBody {
+  static constexpr const char *kName = "ntt";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  const u64 *in;
+  u64 *out;
+  const DevConsts *C;
+  TwRef tw;
+  TabMap map;
+  int limbs;
+  size_t istride, lstride;
+  HD size_t at(int lb) const { return static_cast<size_t>(lb / limbs) * istride + static_cast<size_t>(lb % limbs) * lstride; }
+  HD void phase1(int bid, int, unsigned char *smem) const {
+    constexpr int nt = half_threads(LOGH);
+    const int h = bid & 1, lb = bid >> 1, tab = map.id[lb % limbs];
+    double *fm = reinterpret_cast<double *>(smem);
+    fwd_half_load_f64<LOGH>(fm, tw.fwd_f(tab), C->qf[tab], C->qinvf[tab], h, nt, RawU64{in + at(lb)});
+  }
+  HD void phase2(int bid, int, unsigned char *smem, const unsigned char *) const {
+    constexpr int nt = half_threads(LOGH);
+    constexpr int S = 1 << LOGH;
+    const int h = bid & 1, lb = bid >> 1, tab = map.id[lb % limbs];
+    double *fm = reinterpret_cast<double *>(smem);
+    const double qd = C->qf[tab], qi = C->qinvf[tab];
+    fwd_half_passes_f64<LOGH>(fm, tw.fwd_f(tab), qd, qi, h, nt);
+    u64 *dst = out + at(lb) + static_cast<size_t>(h) * S;
+    FOR_THREADS(tid, nt) {
+#pragma unroll 4
+      for (int j = tid; j < S; j += nt) dst[j] = f_canonical(fm[pidx(j)], qd, qi);
+    }
+  }
+};
+
 struct PlanScaled {  // NttBody's inverse branch: out = INTT(in) (scaled by 1/N, canonical)
   static constexpr const char *kName = "ntt";
   const u64 *in;
