@@ -59,6 +59,7 @@ def config(args, world):
                     f"{'BSGS' if args.bsgs else 'diagonal (reference default use_bsgs=false)'} affine layers",
         "N": N, "t": common.T, "coeff_modulus": "BFVDefault(16384): L=8 data limbs + special prime",
         "blocks_per_gpu_per_step": args.blocks, "use_bsgs": bool(args.bsgs), "parallelism": f"shard{world}",
+        "arith": "exact mod-q arithmetic on u64 residues: error-free FP64-pipe products for the 48/49-bit coefficient primes, integer Shoup products for the 61-bit BEHZ primes",
         "l2": "working set per step (>=0.6 GB of ciphertext state + 144 MB of key-switching keys) exceeds the 126 MB L2",
     }
 
@@ -313,6 +314,25 @@ def main():
             res[name] = {"GBps": limbs * 16 * N / t / 1e6, "limb_transforms_per_s": limbs / t * 1e3, "frac_of_hbm_peak": limbs * 16 * N / t / 1e6 / peak_hbm()[0]}
         ntt_info = {"limbs_per_launch": limbs, "bytes_per_limb": 16 * N, "fwd": res["fwd"], "inv": res["inv"],
                     "note": "exact 49-bit modular transforms on the FP64 pipe (7 FP64 + 1 FRND per butterfly): pipe ceiling = 23 M limbs/s = 6.1 TB/s equivalent"}
+    # ---- the final gather of the result ciphertexts themselves to rank 0 over NCCL/NVLink, outside the timed steps:
+    # the steps gather digests only (65,536 result ciphertexts are 128 GiB); a caller that wants the ciphertexts pays this once ----
+    gather_info = None
+    if world > 1:
+        shard = __import__("importlib").import_module(common.PKG + ".shard")
+        shard.gather_ciphertexts(d_out, world)  # warm-up (communicator setup)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        got = shard.gather_ciphertexts(d_out, world)
+        g1.record()
+        torch.cuda.synchronize()
+        g_ms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            nbytes = (world - 1) * d_out.numel() * 8
+            gather_info = {"ciphertexts": world * B, "bytes_received_by_rank0": nbytes, "ms": float(g_ms.item()),
+                           "GBps": nbytes / float(g_ms.item()) / 1e6, "rank0_block0_matches": bool(torch.equal(got[0], d_out[0]))}
+        del got
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -367,7 +387,7 @@ def main():
         "data": "synthetic", "config": config(args, world), "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(ek_host.numel() * 8 + sym_host.numel() * 8 + B * 12),
                 "d2h_bytes_per_step": int(out_host.numel() * 8)},
-        "gpu_launches": int(launches), "clocks": clocks, "verified": checked, "ntt": ntt_info,
+        "gpu_launches": int(launches), "clocks": clocks, "verified": checked, "ntt": ntt_info, "gather": gather_info,
     }
     print(json.dumps(out))
 

@@ -39,6 +39,41 @@ def gather_digests(local, world):
     return np.concatenate([b.cpu().numpy().view(np.uint64) for b in bufs])
 
 
+def gather_ciphertexts(local, world, dst=0):
+    """The final gather of result ciphertexts to rank `dst` (NCCL over NVLink on GPUs, gloo in the CPU tests).
+    `local`: this rank's ciphertexts, a numpy uint64 array or a torch int64 tensor (device tensors stay on the device),
+    shape [n_r, ...]. Ranks may hold different counts. Returns the concatenation in rank order on `dst`, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    as_numpy = isinstance(local, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(local).view(np.int64)) if as_numpy else local.contiguous()
+    if dist.get_backend() == "nccl" and not t.is_cuda:
+        t = t.cuda()
+    rank = dist.get_rank()
+    counts = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+    counts = [int(c.item()) for c in counts]
+    tail = tuple(t.shape[1:])
+    if len(set(counts)) == 1:
+        bufs = [torch.empty((counts[0],) + tail, dtype=t.dtype, device=t.device) for _ in range(world)] if rank == dst else None
+        dist.gather(t, bufs, dst=dst)
+    else:  # ragged shards: point-to-point into rank dst
+        bufs = None
+        if rank == dst:
+            bufs = [torch.empty((c,) + tail, dtype=t.dtype, device=t.device) for c in counts]
+            bufs[dst].copy_(t)
+            for src in range(world):
+                if src != dst and counts[src]:
+                    dist.recv(bufs[src], src=src)
+        elif t.shape[0]:
+            dist.send(t, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.cat(bufs, dim=0)
+    return out.cpu().numpy().view(np.uint64) if as_numpy else out
+
+
 def _uneven_all_gather(bufs, t):
     import torch.distributed as dist
 

@@ -25,8 +25,12 @@ for name, kind in (("gk_m1", 0), ("gk_p128", 0), ("gk_col", 0), ("rk", 2)):
 words, first, nblk = shard.shard_stream(fx["sym_ct"], rank, world)
 out = ctx.pasta3_decompose(fx["enc_key"], words, first_counter=first) if nblk else np.zeros((0, 2, ctx.L, ctx.N), dtype=np.uint64)
 dig = shard.gather_digests(shard.digest(out) if nblk else np.zeros(0, dtype=np.uint64), world)
+cts = shard.gather_ciphertexts(out, world)  # the final gather of the result ciphertexts themselves
 if rank == 0:
     np.save(os.environ["HHE_OUT"], dig)
+    np.save(os.environ["HHE_OUT"] + ".cts.npy", cts)
+else:
+    assert cts is None
 dist.destroy_process_group()
 '''
 
@@ -58,3 +62,40 @@ def test_two_ranks_equal_one_rank(tmp_path):
         assert p.wait(timeout=600) == 0
     got = np.load(out)
     assert np.array_equal(got, want)
+    assert np.array_equal(np.load(str(out) + ".cts.npy"), fx["decomposed"])  # gathered ciphertexts == the reference's, in block order
+
+
+RAGGED_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["HHE_ROOT"]); sys.path.insert(0, os.path.join(os.environ["HHE_ROOT"], "tests"))
+import common, importlib
+shard = importlib.import_module(common.PKG + ".shard")
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HHE_PORT"], rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+total = 5  # 5 units over 2 ranks: 3 + 2
+lo, hi = shard.block_range(total, rank, world)
+local = (np.arange(lo, hi, dtype=np.uint64)[:, None, None] * 1000 + np.arange(6, dtype=np.uint64).reshape(2, 3)[None])
+out = shard.gather_ciphertexts(local, world)
+empty = shard.gather_ciphertexts(local[:0] if rank else local, world)  # a rank with nothing to contribute
+if rank == 0:
+    want = np.arange(total, dtype=np.uint64)[:, None, None] * 1000 + np.arange(6, dtype=np.uint64).reshape(2, 3)[None]
+    assert np.array_equal(out, want), out
+    assert np.array_equal(empty, want[:3]), empty
+    open(os.environ["HHE_OUT"], "w").write("ok")
+dist.destroy_process_group()
+'''
+
+
+def test_gather_ciphertexts_ragged_shards(tmp_path):
+    script = tmp_path / "ragged.py"
+    script.write_text(RAGGED_WORKER)
+    out = tmp_path / "ok.txt"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", HHE_ROOT=common.ROOT, HHE_PORT="29654", HHE_OUT=str(out))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    assert out.read_text() == "ok"
