@@ -1696,7 +1696,7 @@ struct InvClusterBody {
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[tab], qi = C->qinvf[tab];
     FOR_THREADS(tid, nt) {
-#pragma unroll 4
+#pragma unroll 8
       for (int j = tid; j < S; j += nt) fm[pidx(j)] = u_to_f(src[j]);
     }
     SYNC();
@@ -1713,11 +1713,26 @@ struct InvClusterBody {
     const double w = tw.inv_f(tab).idx[1];
     const auto st = plan.store(lb, C, 2 * S);
     FOR_THREADS(tid, nt) {
-#pragma unroll 2
-      for (int j = h * (S / 2) + tid; j < (h + 1) * (S / 2); j += nt) {
-        const double a = lo[pidx(j)], b = hi[pidx(j)];  // |.| <= 4.5q
-        st.store(j, f_add(a, b));
-        st.store(j + S, f_mulmod_var(f_add(a, -b), w, qd, qi));
+      // one of the two operands comes from the partner CTA over distributed shared memory (long latency): issue the loads of
+      // U butterflies before the first use
+      constexpr int U = 4;
+      const int end = (h + 1) * (S / 2);
+      for (int j0 = h * (S / 2) + tid; j0 < end; j0 += nt * U) {
+        double a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt < end ? j0 + u * nt : j0;
+          a[u] = lo[pidx(j)];  // |.| <= 4.5q
+          b[u] = hi[pidx(j)];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u * nt;
+          if (j < end) {
+            st.store(j, f_add(a[u], b[u]));
+            st.store(j + S, f_mulmod_var(f_add(a[u], -b[u]), w, qd, qi));
+          }
+        }
       }
     }
   }

@@ -102,6 +102,42 @@ def test_records_sharing_counter_zero(world):
         assert np.array_equal(ref.decrypt(got[r])[0][:128], pts[r])
 
 
+def test_siesta_shaped_records_regrouped_by_counter(world):
+    """SURVEY.md 8d config 4, real-data variant: records of 300 words = 3 blocks each, counters 0..2 restarting per record
+    (src/examples/CSP/CSP.cpp:247-252). The engine regroups the 12 blocks into 3 shared-counter batches; every ciphertext must
+    equal the one a single-record call produces, sit at its record-major position, and decrypt (SEAL) to the record."""
+    ref, ctx, rng, key = world["ref"], world["ctx"], world["rng"], world["key"]
+    recs = rng.integers(0, 32, (4, 300), dtype=np.uint64)
+    syms = np.stack([O.pasta_plain(key, common.T, r) for r in recs])
+    got = ctx.pasta3_decompose(world["enc_key"], syms.reshape(-1), records=4).reshape(4, 3, 2, ctx.L, N)
+    alone = ctx.pasta3_decompose(world["enc_key"], syms[2])
+    assert np.array_equal(got[2], alone)
+    assert np.array_equal(got[0, 1], ref.pasta_decompose(world["enc_key"], syms[0][:256])[1])  # SEAL's own block 1
+    for r in range(4):
+        for b in range(3):
+            n = min(128, 300 - 128 * b)
+            assert np.array_equal(ref.decrypt(got[r, b])[0][:n], recs[r, 128 * b:128 * b + n]), (r, b)
+
+
+def test_full_bench_batch_every_block_decrypts(world):
+    """The bench's batch (296 distinct-counter blocks in lock-step): every output ciphertext decrypts under SEAL to its PASTA
+    plaintext with a healthy noise budget, and the batch equals two half-size calls (checksum of checksums)."""
+    ref, ctx, rng, key = world["ref"], world["ctx"], world["rng"], world["key"]
+    B = 296
+    pt = rng.integers(0, common.T, B * 128, dtype=np.uint64)
+    sym = O.pasta_plain(key, common.T, pt)
+    ctx.set_batch(B)
+    got = ctx.pasta3_decompose(world["enc_key"], sym)
+    for b in range(B):
+        slots, budget = ref.decrypt(got[b])
+        assert budget > 60 and np.array_equal(slots[:128], pt[128 * b:128 * (b + 1)]), b
+    ctx.set_batch(B // 2)
+    halves = ctx.pasta3_decompose(world["enc_key"], sym)
+    ctx.set_batch(0)
+    dig = lambda a: a.reshape(a.shape[0], -1).sum(axis=1, dtype=np.uint64)  # noqa: E731
+    assert np.array_equal(dig(got), dig(halves)) and int(dig(got).sum(dtype=np.uint64)) == int(dig(halves).sum(dtype=np.uint64))
+
+
 def test_n32768_primitives_bit_exact_with_seal():
     """BASELINE.json configs[4] (primitive sweep) at N=32768, BFVDefault (L=15 + special): NTT, rotate, relinearize, multiply."""
     NN = 32768
