@@ -2,6 +2,7 @@
 // Layouts: ciphertext batch u64[count][size][L][N]; key-switch accumulators u64[count][2][K][N];
 // key-switching keys W2[L][2][K][N] (value + Shoup quotient, NTT form); twiddles W2[table][fwd|inv][N].
 #pragma once
+#include <type_traits>
 #include "devconsts.h"
 #include "ntt_core.h"
 #include "tmem.h"
@@ -35,6 +36,11 @@ struct StoreScaled {  // inverse transform output: multiply by N^-1, canonicalis
   HD double load(int) const { return 0.0; }
   HD void store(int i, double v) const { dst[i] = f_canonical(f_mulmod_const(v, ninv, q), q, qinv); }
   HD void group_out(int, const double *) const {}
+  // two-step form used by the cluster kernels: aux(j) issues the global loads store(j, v, aux) needs, so a caller can have
+  // several of them in flight before the first dependent instruction
+  struct Aux {};
+  HD Aux aux(int) const { return Aux{}; }
+  HD void store(int i, double v, const Aux &) const { store(i, v); }
 };
 
 struct LoadCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[special] + half mod q_sp  (Corr0MacBody)
@@ -1524,13 +1530,13 @@ struct Corr0MacHalfBody {
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[i], qi = C->qinvf[i];
     const F64Tw twk = tw.fwd_f(i);
-    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
-    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
     const u64 *a0 = acc + ((item * 2) * K + i) * N + hoff;
     const u64 *cin = c0_in + (item * L + i) * N;
     u64 *cout = c0_out + (item * L + i) * N + hoff;
     const u64 *d = D + item * dstride + static_cast<size_t>(i) * N + hoff;
     u64 *s0 = sum + (item * 2 * L + i) * N + hoff;
+    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
+    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
     const u32 *pm = perm + hoff;
     const D2 isp = C->inv_sp_f[i];
     FOR_THREADS(tid, nt) {
@@ -1580,9 +1586,14 @@ struct StoreModDownGalois {
   int logn;
   HD double load(int) const { return 0.0; }
   HD void group_out(int, const double *) const {}
-  HD void store(int j, double v) const {
+  struct Aux {
+    u64 s;
+  };
+  HD Aux aux(int j) const { return Aux{sp[j]}; }
+  HD void store(int j, double v) const { store(j, v, aux(j)); }
+  HD void store(int j, double v, const Aux &ax) const {
     const double x = f_mulmod_const(v, ninv, q);
-    double t = f_add(u_to_f(sp[j]), half_sp);
+    double t = f_add(u_to_f(ax.s), half_sp);
     if (t >= qsp) t = f_add(t, -qsp);
     const double y = f_add(f_add(x, -t), half_i);  // |y| <= 1.4q + q_sp + q/2 < 5q
     const u64 c = f_canonical(f_mulmod_const(y, isp, q), q, qinv);
@@ -1632,13 +1643,18 @@ struct StoreModDownAdd {
   double q, qinv, qsp, half_sp, half_i;
   HD double load(int) const { return 0.0; }
   HD void group_out(int, const double *) const {}
-  HD void store(int j, double v) const {
+  struct Aux {
+    u64 s, b;
+  };
+  HD Aux aux(int j) const { return Aux{sp[j], base ? base[j] : 0}; }
+  HD void store(int j, double v) const { store(j, v, aux(j)); }
+  HD void store(int j, double v, const Aux &ax) const {
     const double x = f_mulmod_const(v, ninv, q);
-    double t = f_add(u_to_f(sp[j]), half_sp);
+    double t = f_add(u_to_f(ax.s), half_sp);
     if (t >= qsp) t = f_add(t, -qsp);
     const double y = f_add(f_add(x, -t), half_i);  // |y| < 5q
     double c = f_mulmod_const(y, isp, q);          // |c| <= 1.5q
-    if (base) c = f_add(c, u_to_f(base[j]));
+    if (base) c = f_add(c, u_to_f(ax.b));
     out[j] = f_canonical(c, q, qinv);
   }
 };
@@ -1715,22 +1731,28 @@ struct InvClusterBody {
     FOR_THREADS(tid, nt) {
       // one of the two operands comes from the partner CTA over distributed shared memory (long latency): issue the loads of
       // U butterflies before the first use
-      constexpr int U = 4;
+      // and the global operands of the fused store (special-limb residue, addend) likewise: the stores in between keep the
+      // compiler from hoisting those loads on its own
+      using Aux = typename decltype(st)::Aux;
+      constexpr int U = std::is_empty<Aux>::value ? 4 : 2;
       const int end = (h + 1) * (S / 2);
       for (int j0 = h * (S / 2) + tid; j0 < end; j0 += nt * U) {
         double a[U], b[U];
+        Aux x0[U], x1[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * nt < end ? j0 + u * nt : j0;
           a[u] = lo[pidx(j)];  // |.| <= 4.5q
           b[u] = hi[pidx(j)];
+          x0[u] = st.aux(j);
+          x1[u] = st.aux(j + S);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * nt;
           if (j < end) {
-            st.store(j, f_add(a[u], b[u]));
-            st.store(j + S, f_mulmod_var(f_add(a[u], -b[u]), w, qd, qi));
+            st.store(j, f_add(a[u], b[u]), x0[u]);
+            st.store(j + S, f_mulmod_var(f_add(a[u], -b[u]), w, qd, qi), x1[u]);
           }
         }
       }
