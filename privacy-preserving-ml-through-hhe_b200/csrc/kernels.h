@@ -512,17 +512,21 @@ struct KsMacOut {
   HD void store(int, double) const {}
   HD void group_out(int g, const double *x) const {
     const int gi = g / nt;  // which of this thread's groups
+    // The tensor-memory accesses are ordered asm statements the compiler will not move loads across: component 1's key loads are
+    // therefore issued by hand before component 0's store, so their latency overlaps the TMEM round trip.
+    double kv[8], kn[8], a[8];
 #pragma unroll
-    for (int comp = 0; comp < 2; ++comp) {
-      const double *kc = (comp ? k1 : k0) + g;
-      double kv[8], a[8];
+    for (int e = 0; e < 8; ++e) kv[e] = k0[g + static_cast<size_t>(e) * G];
+    tm.ld8(gi * 2, a);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) kv[e] = kc[static_cast<size_t>(e) * G];
-      tm.ld8(gi * 2 + comp, a);
+    for (int e = 0; e < 8; ++e) a[e] = f_add(a[e], f_mulmod_var(x[e], kv[e], q, qi));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = f_add(a[e], f_mulmod_var(x[e], kv[e], q, qi));
-      tm.st8(gi * 2 + comp, a);
-    }
+    for (int e = 0; e < 8; ++e) kn[e] = k1[g + static_cast<size_t>(e) * G];
+    tm.st8(gi * 2, a);
+    tm.ld8(gi * 2 + 1, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = f_add(a[e], f_mulmod_var(x[e], kn[e], q, qi));
+    tm.st8(gi * 2 + 1, a);
   }
 };
 
