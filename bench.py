@@ -96,13 +96,13 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
         return
     from oracle import refshim as R
     if not R.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhhe_ref.so was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libhhe_ref.so was not built (needs /root/reference at build time)"})
         return
     cores = os.cpu_count() or 1
     steps = [0, -1, 128] + ([-16 * k for k in range(1, 8)] if args.bsgs else [])
@@ -117,13 +117,13 @@ def run_reference(args, rank):
         total += ref.bench_decompose(enc_key, cores, per, args.bsgs)
     value = cores * per * args.steps / total
     sample = f"{cores} threads x {per} block(s) per step, one pasta::PASTA_SEAL per thread (src/pasta/pasta_3_seal.cpp:106-172 + libseal-4.0.a)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -140,8 +140,17 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly ONE JSON line (rank 0): everything libraries print at the C level (NCCL's version banner ignores
+    # NCCL_DEBUG_FILE at NCCL_DEBUG=VERSION) is sent to stderr for the whole run; the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, emit)
 
     import torch
     import torch.distributed as dist
@@ -149,7 +158,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from oracle import refshim as R
     ref_ok = R.available()
@@ -390,7 +398,7 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 8)},
         "gpu_launches": int(launches), "clocks": clocks, "verified": checked, "ntt": ntt_info, "gather": gather_info,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
