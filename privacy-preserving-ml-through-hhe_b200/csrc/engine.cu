@@ -285,9 +285,9 @@ void Engine::negate(const u64 *a, u64 *out, size_t items) {
   dev_.launch(body, ew_grid(total), kEwThreads, 0);
 }
 
-void Engine::add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first) {
+void Engine::add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx) {
   const size_t total = items * ct_words();
-  AddPlainBody body{a, pt, pstride, out, dC_, negate_first ? 1 : 0, total};
+  AddPlainBody body{a, pt, pstride, out, dC_, negate_first ? 1 : 0, total, ptidx};
   dev_.launch(body, ew_grid(total), kEwThreads, 0);
 }
 
@@ -329,17 +329,17 @@ void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
 }
 
 void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps, size_t sum_off,
-                     u64 *ntt_out) {
+                     u64 *ntt_out, const u32 *didx) {
   require_whole_limb("multiply_plain");
   if (half_fwd_) {
     HHE_DISPATCH_LOG(P_.logn - 1, {
-      NttMacHalfBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out};
+      NttMacHalfBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out, didx};
       dev_.launch(body, items * comps * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
     });
     return;
   }
   HHE_DISPATCH_LOG(P_.logn, {
-    NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out};
+    NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out, didx};
     dev_.launch(body, items * comps * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
 }
@@ -575,10 +575,10 @@ const u64 *Engine::feistel_mask_ntt() {
 }
 
 // PASTA_SEAL::diagonal (src/pasta/pasta_3_seal.cpp:370-413); the 128 products are summed in the NTT domain.
-void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, bool shared) {
+void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx) {
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(P_.L) * N;
-  const size_t nd = shared ? 1 : nb, ds = shared ? 0 : dw;  // diagonals: one set per block, or one for the whole batch
+  const size_t ds = dw;  // diagonals: one set per distinct counter (nd of them), blocks find theirs through didx
   u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nd * N), *D = scratch(nd * dw);
   if (N / 2 != kPastaT) {
     rotate_rows(state, kPastaT, 0, tmp, nb);
@@ -594,7 +594,7 @@ void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, b
     }
     encode_material(mat, nullptr, kDiag, layer, i, pt, nd);
     lift_ntt(pt, D, nd);
-    ntt_mac(cur, D, ds, sum, nb, i == 0);
+    ntt_mac(cur, D, ds, sum, nb, i == 0, 2, 0, nullptr, didx);
   }
   ntt(sum, state, nb, 2 * P_.L, map_mod(2 * P_.L, P_.L, 0), true);
 }
@@ -602,11 +602,11 @@ void Engine::affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, b
 // Same computation with the rotating state kept NTT-resident (see kernels.h "NTT-resident rotation chain"): per
 // rotation 64 + 10 + 8 + 8 limb transforms instead of 72 + 18 + 16. Used when every coefficient prime is on the FP64
 // path; bit-identical to affine_diagonal (tests/test_engine_parity.py compares both rings with the oracle).
-void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, bool shared) {
+void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx) {
   Scope sc(*this);
   const int L = P_.L, K = P_.K;
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(L) * N;
-  const size_t nd = shared ? 1 : nb, ds = shared ? 0 : dw;
+  const size_t ds = dw;
   u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nd * N), *D = scratch(nd * dw);
   u64 *stn = scratch(nb * ctw), *c0a = scratch(nb * dw), *c0b = scratch(nb * dw), *c1c = scratch(nb * dw), *c1n = scratch(nb * dw),
       *g1 = scratch(nb * dw), *acc = scratch(nb * 2 * K * N);
@@ -621,7 +621,7 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   // step 0: sum = NTT(state) * D_0, keeping NTT(state)
   encode_material(mat, nullptr, kDiag, layer, 0, pt, nd);
   lift_ntt(pt, D, nd);
-  ntt_mac(state, D, ds, sum, nb, true, 2, 0, stn);
+  ntt_mac(state, D, ds, sum, nb, true, 2, 0, stn, didx);
   strided_copy(stn, ctw, c0a, dw, dw, nb);
   strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
   strided_copy(state + dw, ctw, c1c, dw, dw, nb);
@@ -654,27 +654,27 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     lift_ntt(pt, D, nd);
     if (half_fwd_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
-        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds};
+        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx};
         dev_.launch(body, nb * L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     } else {
       HHE_DISPATCH_LOG(P_.logn, {
-        Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds};
+        Corr0MacBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx};
         dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     }
     std::swap(c0_in, c0_out);
-    ntt_mac(c1c, D, ds, sum, nb, false, 1, dw, c1n);
+    ntt_mac(c1c, D, ds, sum, nb, false, 1, dw, c1n, didx);
   }
   ntt(sum, state, nb, 2 * L, map_mod(2 * L, L, 0), true);
 }
 
 // PASTA_SEAL::babystep_giantstep (src/pasta/pasta_3_seal.cpp:267-366), N1 = 16, N2 = 8
-void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, bool shared) {
+void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx) {
   constexpr int N1 = 16, N2 = 8;
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(P_.L) * N;
-  const size_t nd = shared ? 1 : nb, ds = shared ? 0 : dw;
+  const size_t ds = dw;
   u64 *tmp = scratch(nb * ctw), *inner = scratch(nb * ctw), *outer = scratch(nb * ctw), *pt = scratch(nd * N),
       *D = scratch(nd * dw), *rot = scratch(nb * ctw * N1);
   if (N / 2 != kPastaT) {
@@ -690,7 +690,7 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, bool 
     for (int j = 0; j < N1; ++j) {
       encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt, nd);
       lift_ntt(pt, D, nd);
-      DyadicMacBody mac{rot + j * nb * ctw, D, inner, dC_, j == 0 ? 1 : 0, nb * ctw, ds};
+      DyadicMacBody mac{rot + j * nb * ctw, D, inner, dC_, j == 0 ? 1 : 0, nb * ctw, ds, didx};
       dev_.launch(mac, ew_grid(nb * ctw), kEwThreads, 0);
     }
     if (k == 0) {
@@ -717,27 +717,24 @@ void Engine::feistel(u64 *state, size_t nb) {
   add(state, rot, state, nb);
 }
 
-void Engine::pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb,
-                         u64 nonce, bool use_bsgs, bool shared, u64 *d_out) {
+void Engine::pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb, size_t nd,
+                         const u32 *didx, u64 nonce, bool use_bsgs, u64 *d_out) {
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N;
-  // `shared`: every block of the batch has the same SHAKE counter (records restart at counter 0), so the
-  // round material, the encoded diagonals and their lifted transforms are computed once and read by all blocks.
-  const size_t nm = shared ? 1 : nb;
   u64 *state = scratch(nb * ctw), *tmp = scratch(nb * ctw), *pt = scratch(nb * N);
-  u32 *mat = reinterpret_cast<u32 *>(scratch((nm * kMaterialWords + 1) / 2));
+  u32 *mat = reinterpret_cast<u32 *>(scratch((nd * kMaterialWords + 1) / 2));
   feistel_mask_ntt();
-  material(d_counters, nm, nonce, mat);
+  material(d_counters, nd, nonce, mat);
   broadcast(d_enc_key, state, ctw, nb);
   for (int layer = 0; layer < 4; ++layer) {
     if (use_bsgs)
-      affine_bsgs(state, mat, layer, nb, shared);
+      affine_bsgs(state, mat, layer, nb, nd, didx);
     else if (compact_keys_ && !getenv_flag("HHE_NO_RESIDENT"))
-      affine_diagonal_resident(state, mat, layer, nb, shared);
+      affine_diagonal_resident(state, mat, layer, nb, nd, didx);
     else
-      affine_diagonal(state, mat, layer, nb, shared);
-    encode_material(mat, nullptr, kRc, layer, 0, pt, nm);  // add_rc (:205-211)
-    add_plain(state, pt, shared ? 0 : N, state, nb, false);
+      affine_diagonal(state, mat, layer, nb, nd, didx);
+    encode_material(mat, nullptr, kRc, layer, 0, pt, nd);  // add_rc (:205-211)
+    add_plain(state, pt, N, state, nb, false, didx);
     rotate_columns(state, 0, tmp, nb);  // mix (:417-423)
     add(tmp, state, tmp, nb);
     add(state, tmp, state, nb);
@@ -765,53 +762,38 @@ void Engine::pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *
   const size_t step = static_cast<size_t>(std::max(1, batch_)), ctw = ct_words();
   u64 *d_ctr = scratch(std::min(step, nblocks));
   // Blocks with equal SHAKE counters (records restart at counter 0: CSP.cpp:247-252) have identical round
-  // matrices and constants. They are regrouped into batches of one counter each, which compute the round material, the encoded
-  // diagonals and their lifted transforms once per batch instead of once per block; the remaining blocks form ordinary batches.
-  std::map<u64, std::vector<u32>> by_counter;
-  if (!getenv_flag("HHE_NO_SHARED_MATERIAL") && nblocks < (static_cast<size_t>(1) << 32))
-    for (size_t b = 0; b < nblocks; ++b) by_counter[counters[b]].push_back(static_cast<u32>(b));
-  if (by_counter.empty() || by_counter.size() == nblocks) {  // all counters distinct: blocks are processed where they lie
-    for (size_t off = 0; off < nblocks; off += step) {
-      const size_t nb = std::min(step, nblocks - off);
+  // matrices and constants: per lock-step batch the round material, the encoded diagonals and their lifted transforms are computed
+  // once per DISTINCT counter, and every block reads its counter's copy through an index (didx).
+  const bool share = !getenv_flag("HHE_NO_SHARED_MATERIAL");
+  u32 *d_idx = reinterpret_cast<u32 *>(scratch((std::min(step, nblocks) + 1) / 2));
+  std::vector<u64> uniq;
+  std::vector<u32> idx;
+  for (size_t off = 0; off < nblocks; off += step) {
+    const size_t nb = std::min(step, nblocks - off);
+    uniq.clear();
+    idx.resize(nb);
+    std::map<u64, u32> seen;
+    for (size_t b = 0; b < nb; ++b) {
+      const u64 c = counters[off + b];
+      auto it = share ? seen.find(c) : seen.end();
+      if (it == seen.end()) {
+        idx[b] = static_cast<u32>(uniq.size());
+        if (share) seen.emplace(c, idx[b]);
+        uniq.push_back(c);
+      } else {
+        idx[b] = it->second;
+      }
+    }
+    const size_t nd = uniq.size();
+    if (nd == nb) {  // all distinct: the caller's array is the list of counters
       dev_.h2d(d_ctr, counters.data() + off, nb * 8);
-      pasta_batch(d_enc_key, d_sym + off * kPastaT, d_lens + off, d_ctr, nb, nonce, use_bsgs, false, d_out + off * ctw);
+    } else {
+      dev_.h2d(d_ctr, uniq.data(), nd * 8);
+      dev_.h2d(d_idx, idx.data(), nb * 4);
+      dev_.sync();  // uniq / idx are reused by the next batch
     }
-    return;
-  }
-  std::vector<u32> singles;
-  std::vector<std::pair<std::vector<u32>, bool>> batches;  // (block indices, shared)
-  for (auto &kv : by_counter) {
-    if (kv.second.size() == 1) {
-      singles.push_back(kv.second[0]);
-      continue;
-    }
-    for (size_t off = 0; off < kv.second.size(); off += step) {
-      const size_t nb = std::min(step, kv.second.size() - off);
-      batches.emplace_back(std::vector<u32>(kv.second.begin() + off, kv.second.begin() + off + nb), nb > 1);
-    }
-  }
-  std::sort(singles.begin(), singles.end());
-  for (size_t off = 0; off < singles.size(); off += step)
-    batches.emplace_back(std::vector<u32>(singles.begin() + off, singles.begin() + std::min(singles.size(), off + step)), false);
-  const size_t cap = std::min(step, nblocks);
-  u32 *d_idx = reinterpret_cast<u32 *>(scratch((cap + 1) / 2)), *g_lens = reinterpret_cast<u32 *>(scratch((cap + 1) / 2));
-  u64 *g_sym = scratch(cap * kPastaT), *g_out = scratch(cap * ctw);
-  std::vector<u64> ctr;
-  for (auto &bt : batches) {
-    const std::vector<u32> &idx = bt.first;
-    const size_t nb = idx.size();
-    ctr.resize(nb);
-    for (size_t i = 0; i < nb; ++i) ctr[i] = counters[idx[i]];
-    dev_.h2d(d_ctr, ctr.data(), nb * 8);
-    dev_.h2d(d_idx, idx.data(), nb * 4);
-    dev_.sync();  // ctr / idx live on the host stack of this loop
-    GatherRowsBody<u64> gs{d_sym, g_sym, d_idx, static_cast<size_t>(kPastaT), nb * kPastaT, 0};
-    dev_.launch(gs, ew_grid(nb * kPastaT), kEwThreads, 0);
-    GatherRowsBody<u32> gl{d_lens, g_lens, d_idx, 1, nb, 0};
-    dev_.launch(gl, ew_grid(nb), kEwThreads, 0);
-    pasta_batch(d_enc_key, g_sym, g_lens, d_ctr, nb, nonce, use_bsgs, bt.second, g_out);
-    GatherRowsBody<u64> so{g_out, d_out, d_idx, ctw, nb * ctw, 1};
-    dev_.launch(so, ew_grid(nb * ctw), kEwThreads, 0);
+    pasta_batch(d_enc_key, d_sym + off * kPastaT, d_lens + off, d_ctr, nb, nd, nd < nb ? d_idx : nullptr, nonce, use_bsgs,
+                d_out + off * ctw);
   }
 }
 

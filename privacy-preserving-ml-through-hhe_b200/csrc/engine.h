@@ -46,13 +46,13 @@ class Engine {
            size_t limb_stride = 0);
   void add(const u64 *a, const u64 *b, u64 *out, size_t items, int size = 2);
   void negate(const u64 *a, u64 *out, size_t items);
-  void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first);
+  void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx = nullptr);
   void broadcast(const u64 *src, u64 *out, size_t words, size_t items);
   void encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items);
   void encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items);
   void lift_ntt(const u64 *pt, u64 *D, size_t items);
   void ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps = 2, size_t sum_off = 0,
-               u64 *ntt_out = nullptr);
+               u64 *ntt_out = nullptr, const u32 *didx = nullptr);
   void ct_intt(u64 *ct, size_t items, int size = 2);
   void multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items);
   void galois(const u64 *a, u32 elt, u64 *out, size_t items);
@@ -84,12 +84,14 @@ class Engine {
  private:
   friend struct Scope;
   void arena_restore(size_t chunk, size_t used);
-  void pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb, u64 nonce,
-                   bool use_bsgs, bool shared, u64 *d_out);
-  void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, bool shared);
-  void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, bool shared);
+  // d_counters: the `nd` distinct SHAKE counters of the batch; didx (device, nb entries, null when nd == nb): block -> index
+  // of its counter. Blocks with equal counters share round material, encoded diagonals and their lifted transforms.
+  void pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const u64 *d_counters, size_t nb, size_t nd,
+                   const u32 *didx, u64 nonce, bool use_bsgs, u64 *d_out);
+  void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
+  void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
   const u32 *ntt_perm(u32 elt);
-  void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, bool shared);
+  void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
   void feistel(u64 *state, size_t nb);
   const W2 *need_key(int kind, u32 elt) const;
   void require_whole_limb(const char *what) const;

@@ -928,6 +928,7 @@ struct AddPlainBody {
   const DevConsts *C;
   int negate;
   size_t total;  // count*2*L*N
+  const u32 *ptidx;  // optional: item -> plaintext index (blocks sharing a SHAKE counter share round constants)
   HD void operator()(int bid, int nt, unsigned char *) const {
     const size_t N = C->N;
     const int L = C->L;
@@ -943,7 +944,7 @@ struct AddPlainBody {
         u64 v = a[g];
         if (negate) v = neg_mod(v, mi.q);
         if (comp == 0) {
-          const u64 m = pt[item * pstride + j];
+          const u64 m = pt[(ptidx ? ptidx[item] : item) * pstride + j];
           const u64 fix = (m * C->q_mod_t + C->half_t) / C->t;  // m, Q mod t < 2^32
           v = add_mod(v, mul_add_mod(m, C->q_div_t_mod_q[i], fix, mi), mi.q);
         }
@@ -1106,6 +1107,7 @@ struct NttMacBody {
   int comps;  // polynomials per item in `ct` (2: whole ciphertexts, 1: one component)
   size_t sum_stride, sum_off;  // sum limb (item, c, i) lives at sum + item*sum_stride + sum_off + (c*L + i)*N
   u64 *ntt_out;                // optional: NTT_i(ct) itself (canonical), same indexing as ct
+  const u32 *didx;  // optional: item -> diagonal index (blocks sharing a SHAKE counter share their diagonals)
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     u64 *sm = reinterpret_cast<u64 *>(smem);
@@ -1115,7 +1117,7 @@ struct NttMacBody {
     const DevMod mi = C->mod[i];
     const u64 q = mi.q;
     const u64 *src = ct + static_cast<size_t>(bid) * S;
-    const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
+    const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * S;
     u64 *dst = sum + item * sum_stride + sum_off + static_cast<size_t>(cl) * S;
     u64 *nout = ntt_out ? ntt_out + static_cast<size_t>(bid) * S : nullptr;
     if (C->f64[i]) {
@@ -1161,6 +1163,7 @@ struct DyadicMacBody {
   int first;
   size_t total;  // items * 2 * L * N
   size_t dstride;
+  const u32 *didx;  // optional: item -> diagonal index
   HD void operator()(int bid, int nt, unsigned char *) const {
     const size_t N = C->N;
     const u32 L = static_cast<u32>(C->L);
@@ -1170,7 +1173,7 @@ struct DyadicMacBody {
         const u32 limb = static_cast<u32>(g >> C->logn);
         const u32 i = limb % L, item = limb / (2 * L);
         const DevMod mi = C->mod[i];
-        u64 v = mul_mod(a[g], D[static_cast<size_t>(item) * dstride + static_cast<size_t>(i) * N + (g & (N - 1))], mi);
+        u64 v = mul_mod(a[g], D[static_cast<size_t>(didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + (g & (N - 1))], mi);
         if (!first) v = add_mod(v, sum[g], mi.q);
         sum[g] = v;
       }
@@ -1315,29 +1318,6 @@ struct StridedCopyBody {
   }
 };
 
-// Row gather / scatter by index (blocks regrouped by SHAKE counter, Engine::pasta_decompose): units of `unit` bytes' worth of T
-template <class T>
-struct GatherRowsBody {
-  static constexpr const char *kName = "gather_rows";
-  const T *src;
-  T *dst;
-  const u32 *idx;  // [rows]
-  size_t words, total;  // total = rows * words
-  int scatter;     // 0: dst[r] = src[idx[r]]   1: dst[idx[r]] = src[r]
-  HD void operator()(int bid, int nt, unsigned char *) const {
-    FOR_THREADS(tid, nt) {
-      const size_t g = static_cast<size_t>(bid) * nt + tid;
-      if (g < total) {
-        const size_t r = g / words, w = g % words, o = static_cast<size_t>(idx[r]) * words + w;
-        if (scatter)
-          dst[o] = src[g];
-        else
-          dst[g] = src[o];
-      }
-    }
-  }
-};
-
 // ModDown of component 1 only: c1[i][j] = (acc1[i][j] - (r1[j] mod q_i) + half_i) * q_sp^-1, acc1 in coefficient form
 struct ModDownC1Body {
   static constexpr const char *kName = "moddown_c1";
@@ -1379,6 +1359,7 @@ struct Corr0MacBody {
   const DevConsts *C;
   TwRef tw;
   size_t dstride;     // L*N or 0
+  const u32 *didx;    // optional: item -> diagonal index
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     const int L = C->L, K = C->K, i = bid % L;
@@ -1392,7 +1373,7 @@ struct Corr0MacBody {
     const u64 *a0 = acc + ((item * 2) * K + i) * S;
     const u64 *cin = c0_in + (item * L + i) * S;
     u64 *cout = c0_out + (item * L + i) * S;
-    const u64 *d = D + item * dstride + static_cast<size_t>(i) * S;
+    const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * S;
     u64 *s0 = sum + (item * 2 * L + i) * S;
     FOR_THREADS(tid, nt) {
       constexpr int U = 4;  // independent gathers in flight per thread (perm -> c0 is a dependent pair of loads)
@@ -1469,6 +1450,7 @@ struct NttMacHalfBody {
   int comps;
   size_t sum_stride, sum_off;
   u64 *ntt_out;  // optional: NTT_i(ct) itself (canonical), same indexing as ct
+  const u32 *didx;  // optional: item -> diagonal index (blocks sharing a SHAKE counter share their diagonals)
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
@@ -1477,7 +1459,7 @@ struct NttMacHalfBody {
     const size_t item = lb / (comps * L);
     const int cl = lb % (comps * L);
     const size_t hoff = static_cast<size_t>(h) * S;
-    const u64 *d = D + item * dstride + static_cast<size_t>(i) * (2 * S) + hoff;
+    const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * (2 * S) + hoff;
     u64 *dst = sum + item * sum_stride + sum_off + static_cast<size_t>(cl) * (2 * S) + hoff;
     u64 *nout = ntt_out ? ntt_out + static_cast<size_t>(lb) * (2 * S) + hoff : nullptr;
     double *fm = reinterpret_cast<double *>(smem);
@@ -1523,6 +1505,7 @@ struct Corr0MacHalfBody {
   const DevConsts *C;
   TwRef tw;
   size_t dstride;     // L*N or 0
+  const u32 *didx;    // optional: item -> diagonal index
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
@@ -1537,7 +1520,7 @@ struct Corr0MacHalfBody {
     const u64 *a0 = acc + ((item * 2) * K + i) * N + hoff;
     const u64 *cin = c0_in + (item * L + i) * N;
     u64 *cout = c0_out + (item * L + i) * N + hoff;
-    const u64 *d = D + item * dstride + static_cast<size_t>(i) * N + hoff;
+    const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + hoff;
     u64 *s0 = sum + (item * 2 * L + i) * N + hoff;
     fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
     fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);

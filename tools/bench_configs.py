@@ -109,7 +109,34 @@ def configs123():
     print(json.dumps({"config": 3, "samples": S, "b200_e2e_s": dt, "samples_per_s": S / dt, "spot_check_dot_products": ok,
                       "reference_1core_estimate_s": ref_est, "speedup_vs_1core": ref_est / dt}), flush=True)
 
+def config4_siesta():
+    """SURVEY.md 8d config 4, real-data variant: SIESTA-shaped records (300 words in [0,31] -> 3 blocks, counters 0..2 restarting per
+    record) through the service call hhe_csp_decompose (host buffers: transcipher + flatten per record). The engine regroups the blocks
+    by counter, so the round material and the diagonals of each of the 3 counters are computed once per batch."""
+    N = 16384
+    ref = R.Ref(N, T, None, seed=31, steps=(0, -1, 128, -128, -256), default_gk=False)
+    ctx = pkg.Context(N, T, ref.q, device=0, stream=stream.cuda_stream)
+    common.load_keys_from_ref(ctx, ref, keysets=(0,))
+    for s_ in (-128, -256):
+        ctx.load_ksk(1, ref.galois_elt(s_), ref.ksk(0, ref.galois_elt(s_)))
+    rng = np.random.default_rng(9)
+    key = rng.integers(0, T, 256, dtype=np.uint64)
+    enc_key = ref.encrypt(common.pack_key(key, N))
+    from oracle import oracle as O
+    Rn = int(os.environ.get("SIESTA_RECORDS", 98))  # 98 x 3 = 294 blocks: one lock-step wave
+    recs = rng.integers(0, 32, (Rn, 300), dtype=np.uint64)
+    syms = np.stack([O.pasta_plain(key, T, r) for r in recs])
+    ctx.csp_decompose(enc_key, syms.reshape(-1), records=Rn, flatten_keys=1)
+    t0 = time.perf_counter(); out = ctx.csp_decompose(enc_key, syms.reshape(-1), records=Rn, flatten_keys=1); dt = time.perf_counter() - t0
+    ok = all(np.array_equal(ref.decrypt(out[r])[0][:300], recs[r]) for r in (0, Rn // 2, Rn - 1))
+    blk_s = ref.bench_decompose(enc_key, 1, 1, False); rot_s = ref.bench_primitive(enc_key, 2, 3)
+    print(json.dumps({"config": "4-siesta", "records": Rn, "blocks": 3 * Rn, "b200_e2e_s": dt, "records_per_s": Rn / dt, "blocks_per_s": 3 * Rn / dt,
+                      "records_decrypt_to_input": ok, "reference_1core_estimate_s": Rn * (3 * blk_s + 2 * rot_s),
+                      "speedup_vs_1core": Rn * (3 * blk_s + 2 * rot_s) / dt}), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["5", "123"]
+    which = sys.argv[1:] or ["5", "123", "4"]
     if "5" in which: config5()
     if "123" in which: configs123()
+    if "4" in which: config4_siesta()
