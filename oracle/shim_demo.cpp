@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sstream>
 
 #include "hhe_seal_shim.h"
 #include "pasta_3_plain.h"
@@ -95,6 +96,16 @@ int main(int argc, char **argv) {
     svc_ok = svc_ok && s_res.size() == 1 && s_res[0].size() == 1 && same(s_res[0][0], r_sum);
   }
 
+  // ---- the same keys as serialized gRPC payloads (Analyst.cpp:273-318): parsed and uploaded by the engine's SEAL codec ----
+  std::stringstream rk_ss, gk_ss;
+  rk.save(rk_ss);        // SEAL's default compression (zstd)
+  pasta_gk.save(gk_ss);
+  const size_t n_rk = engine.load_serialized(rk_ss.str(), HHE_RELIN), n_gk = engine.load_serialized(gk_ss.str(), HHE_KEYSET_0);
+  std::vector<uint64_t> first_block(sym.begin(), sym.begin() + std::min<size_t>(128, sym.size()));
+  std::vector<Ciphertext> w_blocks = gpu.decomposition(first_block, enc_key, true);
+  const bool wire_ok = n_rk == 1 && n_gk == 3 && w_blocks.size() == 1 && same(w_blocks[0], r_blocks[0]);
+  svc_ok = svc_ok && wire_ok;
+
   bool ok = svc_ok && r_blocks.size() == g_blocks.size();
   for (size_t b = 0; ok && b < r_blocks.size(); b++) ok = same(r_blocks[b], g_blocks[b]);
   ok = ok && same(r_flat, g_flat) && same(r_prod, g_prod) && same(r_sum, g_sum);
@@ -105,8 +116,8 @@ int main(int argc, char **argv) {
   bool dec_ok = true;
   for (size_t i = 0; i < input_len; i++) dec_ok = dec_ok && slots[i] == plain[i];
   std::printf("{\"N\": %zu, \"blocks\": %zu, \"ciphertexts_identical\": %s, \"decrypts_to_plaintext\": %s, \"noise_budget\": %d, "
-              "\"reference_cpu_s\": %.3f, \"b200_s\": %.3f}\n",
-              N, blocks, ok ? "true" : "false", dec_ok ? "true" : "false", dec.invariant_noise_budget(g_sum),
+              "\"serialized_keys_ok\": %s, \"reference_cpu_s\": %.3f, \"b200_s\": %.3f}\n",
+              N, blocks, ok ? "true" : "false", dec_ok ? "true" : "false", dec.invariant_noise_budget(g_sum), wire_ok ? "true" : "false",
               std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
   return ok && dec_ok ? 0 : 1;
 }
