@@ -666,6 +666,8 @@ int hhe_pasta3_decompose_serialized(hhe_ctx *ctx, const uint8_t *enc_key_bytes, 
     const size_t nblocks = (n_words + kPastaT - 1) / kPastaT;
     std::vector<u64> cts(nblocks * ctw);
     const int rc = hhe_pasta3_decompose(ctx, key.data(), sym_ct, n_words, nonce, first_counter, use_bsgs, cts.data());
+    if (rc == HHE_ERR_INVALID) throw std::invalid_argument(g_error);  // keep the inner call's error class
+    if (rc == HHE_ERR_LOGIC) throw std::logic_error(g_error);
     if (rc != HHE_OK) throw std::runtime_error(g_error);
     size_t o = 0;
     for (size_t b = 0; b < nblocks; ++b) {

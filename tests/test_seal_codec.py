@@ -168,4 +168,10 @@ def test_serialized_keys_and_ciphertexts_through_the_engine(ref, backend):
         assert used == len(b) and np.array_equal(got, w)
         mine, _ = ring.load_ciphertext(b)
         assert np.array_equal(mine, w)
+    # error classes survive the serialized wrapper: a word >= t is std::invalid_argument in the reference (BatchEncoder::encode),
+    # a key ciphertext that is not valid for the parameters is SEAL's std::logic_error
+    with pytest.raises(pkg.HheInvalidArgument):
+        ctx.pasta3_decompose_serialized(ref.ct_save(enc_key, 2), np.array([common.T], dtype=np.uint64))
+    with pytest.raises(pkg.HheLogicError):
+        ctx.pasta3_decompose_serialized(b"\x00" * 64, sym)
     ctx.close()
