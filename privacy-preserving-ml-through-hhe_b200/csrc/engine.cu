@@ -674,9 +674,8 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_
   constexpr int N1 = 16, N2 = 8;
   Scope sc(*this);
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(P_.L) * N;
-  const size_t ds = dw;
-  u64 *tmp = scratch(nb * ctw), *inner = scratch(nb * ctw), *outer = scratch(nb * ctw), *pt = scratch(nd * N),
-      *D = scratch(nd * dw), *rot = scratch(nb * ctw * N1);
+  u64 *tmp = scratch(nb * ctw), *inner = scratch(nb * ctw), *outer = scratch(nb * ctw), *pt = scratch(nd * N1 * N),
+      *D = scratch(nd * N1 * dw), *rot = scratch(nb * ctw * N1);
   if (N / 2 != kPastaT) {
     rotate_rows(state, kPastaT, 0, tmp, nb);
     add(state, tmp, state, nb);
@@ -687,12 +686,12 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_
   // every baby rotation is multiplied with 8 diagonals: transform each once (in place), then the products are element-wise
   ntt(rot, rot, nb * N1, 2 * P_.L, mq, false);
   for (int k = 0; k < N2; ++k) {
-    for (int j = 0; j < N1; ++j) {
-      encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt, nd);
-      lift_ntt(pt, D, nd);
-      DyadicMacBody mac{rot + j * nb * ctw, D, inner, dC_, j == 0 ? 1 : 0, nb * ctw, ds, didx};
-      dev_.launch(mac, ew_grid(nb * ctw), kEwThreads, 0);
-    }
+    // the 16 diagonals of this giant step are encoded, lifted and transformed as one batch ([j][nd] items), then one pass over
+    // the baby rotations forms the inner sum: every residue of `inner` is written once
+    for (int j = 0; j < N1; ++j) encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt + static_cast<size_t>(j) * nd * N, nd);
+    lift_ntt(pt, D, nd * N1);
+    DyadicMacNBody mac{rot, D, inner, dC_, N1, nb * ctw, nd * dw, dw, didx, nb * ctw};
+    dev_.launch(mac, ew_grid(nb * ctw), kEwThreads, 0);
     if (k == 0) {
       ntt(inner, outer, nb, 2 * P_.L, mq, true);
     } else {

@@ -1181,6 +1181,59 @@ struct DyadicMacBody {
   }
 };
 
+// The inner sum of one giant step of PASTA_SEAL::babystep_giantstep in one pass: inner = sum_{j < J} rot_j (.) D_j with the J baby
+// rotations and the J lifted diagonals resident in HBM (pasta_3_seal.cpp:349-357: multiply_plain + add_inplace per j). Each residue
+// of `inner` is produced by one thread and written once: 16 x (2 + 1) MiB read + 2 MiB written per block instead of 16 x 7 MiB.
+struct DyadicMacNBody {
+  static constexpr const char *kName = "dyadic_mac";
+  const u64 *rot;  // [J][items][2][L][N] NTT form
+  const u64 *D;    // [J][nd][L][N]
+  u64 *inner;      // [items][2][L][N]
+  const DevConsts *C;
+  int J;
+  size_t rstride;  // words between consecutive j in rot (items * 2 * L * N)
+  size_t jstride;  // words between consecutive j in D (nd * L * N)
+  size_t dstride;  // L * N
+  const u32 *didx;  // optional: item -> diagonal index
+  size_t total;     // items * 2 * L * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    const u32 L = static_cast<u32>(C->L);
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const u32 limb = static_cast<u32>(g >> C->logn);
+        const u32 i = limb % L, item = limb / (2 * L);
+        const u64 *dp = D + static_cast<size_t>(didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + (g & (N - 1));
+        const u64 *rp = rot + g;
+        if (C->f64[i]) {  // |each product| <= 0.7q, 16 of them stay far below 2^53
+          const double q = C->qf[i], qi = C->qinvf[i];
+          double acc = 0.0;
+          for (int j0 = 0; j0 < J; j0 += 4) {
+            u64 rv[4], dv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + u < J ? j0 + u : j0;
+              rv[u] = rp[static_cast<size_t>(j) * rstride];
+              dv[u] = dp[static_cast<size_t>(j) * jstride];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (j0 + u < J) acc = f_add(acc, f_mulmod_var(u_to_f(rv[u]), u_to_f(dv[u]), q, qi));
+          }
+          inner[g] = f_canonical(acc, q, qi);
+        } else {
+          const DevMod mi = C->mod[i];
+          u64 acc = 0;
+          for (int j = 0; j < J; ++j)
+            acc = add_mod(acc, mul_mod(rp[static_cast<size_t>(j) * rstride], dp[static_cast<size_t>(j) * jstride], mi), mi.q);
+          inner[g] = acc;
+        }
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------------------
 // BEHZ multiplication (Evaluator::bfv_multiply, seal/evaluator.h:214; RNSTool, seal/util/rns.h:213-228)
 
