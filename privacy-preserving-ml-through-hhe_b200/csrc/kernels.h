@@ -1150,37 +1150,6 @@ struct NttMacBody {
   }
 };
 
-// ------------------------------------------------------------------------------------------------------------
-// Element-wise plaintext product in the NTT domain: sum[b][c][i] (+)= a[b][c][i] (.) D[b][i]  (a already transformed).
-// The baby-step/giant-step affine layer transforms each of its 16 baby rotations once and reuses them for all 8
-// giant steps (pasta_3_seal.cpp:349-365 multiplies every rot[j] with 8 different diagonals).
-struct DyadicMacBody {
-  static constexpr const char *kName = "dyadic_mac";
-  const u64 *a;  // [items][2][L][N] NTT form
-  const u64 *D;  // [items][L][N] (dstride = L*N) or shared by all items (dstride = 0)
-  u64 *sum;      // [items][2][L][N]
-  const DevConsts *C;
-  int first;
-  size_t total;  // items * 2 * L * N
-  size_t dstride;
-  const u32 *didx;  // optional: item -> diagonal index
-  HD void operator()(int bid, int nt, unsigned char *) const {
-    const size_t N = C->N;
-    const u32 L = static_cast<u32>(C->L);
-    FOR_THREADS(tid, nt) {
-      const size_t g = static_cast<size_t>(bid) * nt + tid;
-      if (g < total) {
-        const u32 limb = static_cast<u32>(g >> C->logn);
-        const u32 i = limb % L, item = limb / (2 * L);
-        const DevMod mi = C->mod[i];
-        u64 v = mul_mod(a[g], D[static_cast<size_t>(didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + (g & (N - 1))], mi);
-        if (!first) v = add_mod(v, sum[g], mi.q);
-        sum[g] = v;
-      }
-    }
-  }
-};
-
 // The inner sum of one giant step of PASTA_SEAL::babystep_giantstep in one pass: inner = sum_{j < J} rot_j (.) D_j with the J baby
 // rotations and the J lifted diagonals resident in HBM (pasta_3_seal.cpp:349-357: multiply_plain + add_inplace per j). Each residue
 // of `inner` is produced by one thread and written once: 16 x (2 + 1) MiB read + 2 MiB written per block instead of 16 x 7 MiB.
