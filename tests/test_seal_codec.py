@@ -48,6 +48,26 @@ def test_parms_id_bfv_default_16384(ring):
     r.close()
 
 
+def test_full_size_ciphertexts_bfv_default_16384():
+    """BASELINE.json's ring: 2 MiB ciphertexts (and the 3 MiB size-3 form) through every compression mode, both directions."""
+    r = R.Ref(16384, common.T, None, seed=2, steps=(), default_gk=False)
+    big = seal_io.Ring(16384, common.T, common.Q_16384)
+    ct = r.encrypt(np.arange(784, dtype=np.uint64) % 256)
+    assert big.save_ciphertext(ct, seal_io.COMPR_NONE) == r.ct_save(ct, 0)
+    for compr in (0, 1, 2):
+        theirs = r.ct_save(ct, compr)
+        got, used = big.load_ciphertext(theirs)
+        assert used == len(theirs) and np.array_equal(got, ct)
+        back, used = r.ct_load(big.save_ciphertext(ct, compr))
+        assert np.array_equal(back, ct)
+    ct3 = r.multiply(ct, ct)
+    got3, _ = big.load_ciphertext(r.ct_save(ct3, 2))
+    assert got3.shape == (3, 8, 16384) and np.array_equal(got3, ct3)
+    rk = big.unpack_keys(r.keys_save(2, 2))  # the 18 MiB relinearisation key as SEAL ships it (zstd)
+    assert list(rk) == [0] and np.array_equal(rk[0], r.ksk(2))
+    r.close()
+
+
 def test_uncompressed_save_is_byte_identical_to_seal(ref, ring):
     ct = ref.encrypt(np.arange(300, dtype=np.uint64))
     assert ring.save_ciphertext(ct, seal_io.COMPR_NONE) == ref.ct_save(ct, 0)
