@@ -107,6 +107,7 @@ class Engine {
   bool tmem_ks_ = false;  // FP64 key switch with accumulators in tensor memory (keys stored group-major)
   int ks_threads_ = 512;   // CTA size of the tensor-memory key-switch kernel (512 x 64 registers or 256 x 128 registers)
   bool cluster_inv_ = false;  // FP64 inverse transforms as two-CTA clusters (half-limb CTAs, last stage over distributed shared memory)
+  int pf_ntt_ = 0, pf_limbs_ = 0, pf_items_ = 0;  // L2 prefetch distances (limbs: plain transforms / other half-limb kernels; items: ks_digits); 0 = off
   bool half_fwd_ = false;  // FP64 forward transforms of lift_ntt / ntt_mac / corr0_mac as half-limb CTAs (two per SM)
   void launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, u64 *acc, size_t items, const u64 *reuse, size_t reuse_stride,
                         const u32 *perm);  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)

@@ -1,0 +1,177 @@
+// Engine implementation (2/4): transforms, element-wise operations, encode, multiply_plain.
+#include "engine_impl.h"
+
+namespace hhe {
+
+// ------------------------------------------------------------------------------------------------ primitives
+void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap &map, bool inverse, size_t item_stride,
+                 size_t limb_stride) {
+  if (split_) {
+    if (limb_stride) throw std::invalid_argument("strided limbs are not supported by the split transforms");
+    const size_t stride = item_stride ? item_stride : static_cast<size_t>(limbs) * P_.N;
+    Scope sc(*this);
+    if (!inverse && in == out) {
+      // both half-CTAs of a limb read the whole limb: an in-place forward transform needs a private copy of the input
+      const size_t words = (items - 1) * stride + static_cast<size_t>(limbs) * P_.N;
+      u64 *copy = scratch(words);
+      dev_.d2d(copy, in, words * 8);
+      in = copy;
+    }
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      NttSplitBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, stride};
+      dev_.launch(body, items * limbs * 2, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    if (inverse) {
+      const size_t total = items * limbs * (P_.N / 2);
+      InvFinalBody fin{out, dC_, twref(), map, limbs, stride, total};
+      dev_.launch(fin, ew_grid(total), kEwThreads, 0);
+    }
+    return;
+  }
+  if (cluster_inv_) {
+    bool all_f64 = true;
+    for (int l = 0; l < limbs; ++l) all_f64 = all_f64 && table_is_f64(P_, map.id[l]);
+    if (all_f64 && !inverse && !getenv_flag("HHE_NO_FWD_CLUSTER")) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        NttFwdClusterBody<LOGV> body{in, out, dC_, twref(), map, limbs, item_stride ? item_stride : static_cast<size_t>(limbs) << (LOGV + 1),
+                                     limb_stride ? limb_stride : static_cast<size_t>(2) << LOGV, pf_ntt_, static_cast<int>(items * limbs)};
+        dev_.launch_cluster2(body, items * limbs * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+      return;
+    }
+    if (all_f64 && inverse) {
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        using Body = InvClusterBody<LOGV, PlanScaled>;
+        Body body{PlanScaled{in, out, map, limbs, item_stride ? item_stride : static_cast<size_t>(limbs) << (LOGV + 1),
+                             limb_stride ? limb_stride : static_cast<size_t>(2) << LOGV},
+                  dC_, twref(), pf_ntt_, static_cast<int>(items * limbs)};
+        dev_.launch_cluster2(body, items * limbs * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      });
+      return;
+    }
+  }
+  HHE_DISPATCH_LOG(P_.logn, {
+    NttBody<LOGV> body{in, out, dC_, twref(), map, limbs, inverse ? 1 : 0, item_stride ? item_stride : static_cast<size_t>(limbs) << LOGV,
+                        limb_stride ? limb_stride : static_cast<size_t>(1) << LOGV};
+    dev_.launch(body, items * limbs, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+  });
+}
+
+void Engine::require_whole_limb(const char *what) const {
+  if (split_) throw std::invalid_argument(std::string(what) + " is not available at poly_modulus_degree 32768 in this build (NTT, rotate, relinearize, multiply are)");
+}
+
+void Engine::add(const u64 *a, const u64 *b, u64 *out, size_t items, int size) {
+  const size_t total = items * ct_words(size);
+  AddBody body{a, b, out, dC_, size * P_.L, total};
+  dev_.launch(body, ew_grid(total), kEwThreads, 0);
+}
+
+void Engine::negate(const u64 *a, u64 *out, size_t items) {
+  const size_t total = items * ct_words();
+  NegateBody body{a, out, dC_, total};
+  dev_.launch(body, ew_grid(total), kEwThreads, 0);
+}
+
+void Engine::add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx) {
+  const size_t total = items * ct_words();
+  AddPlainBody body{a, pt, pstride, out, dC_, negate_first ? 1 : 0, total, ptidx};
+  dev_.launch(body, ew_grid(total), kEwThreads, 0);
+}
+
+void Engine::broadcast(const u64 *src, u64 *out, size_t words, size_t items) {
+  BroadcastBody body{src, out, words, words * items};
+  dev_.launch(body, ew_grid(words * items), kEwThreads, 0);
+}
+
+void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items) {
+  if (n > P_.N) throw std::invalid_argument("values_matrix size exceeds slot count");
+  require_whole_limb("encode");
+  HHE_DISPATCH_LOG(P_.logn, {
+    EncodeBody<LOGV> body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, twref(), kSlots, 0, 0};
+    dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+  });
+}
+
+void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items) {
+  require_whole_limb("PASTA transciphering");
+  HHE_DISPATCH_LOG(P_.logn, {
+    EncodeBody<LOGV> body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, twref(), mode, layer, diag};
+    dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+  });
+}
+
+void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
+  require_whole_limb("multiply_plain");
+  if (half_fwd_) {
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      LiftNttHalfBody<LOGV> body{pt, D, dC_, twref()};
+      dev_.launch(body, items * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    return;
+  }
+  HHE_DISPATCH_LOG(P_.logn, {
+    LiftNttBody<LOGV> body{pt, D, dC_, twref()};
+    dev_.launch(body, items * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+  });
+}
+
+void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps, size_t sum_off,
+                     u64 *ntt_out, const u32 *didx) {
+  require_whole_limb("multiply_plain");
+  if (half_fwd_) {
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      NttMacHalfBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out, didx,
+                                pf_limbs_, static_cast<int>(items * comps * P_.L)};
+      dev_.launch(body, items * comps * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    });
+    return;
+  }
+  HHE_DISPATCH_LOG(P_.logn, {
+    NttMacBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out, didx};
+    dev_.launch(body, items * comps * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+  });
+}
+
+void Engine::strided_copy(const u64 *src, size_t sstride, u64 *dst, size_t dstride, size_t words, size_t rows) {
+  StridedCopyBody body{src, dst, sstride, dstride, words, words * rows};
+  dev_.launch(body, ew_grid(words * rows), kEwThreads, 0);
+}
+
+// Permutation of NTT slots induced by X -> X^elt: slot i holds a(psi^(2*bitrev(i)+1)), so galois(a) at slot i is a at
+// the slot whose exponent is (2*bitrev(i)+1)*elt mod 2N  (cf. GaloisTool::apply_galois_ntt, seal/util/galois.h:78).
+const u32 *Engine::ntt_perm(u32 elt) {
+  auto it = perms_.find(elt);
+  if (it != perms_.end()) return it->second;
+  const u64 N = P_.N, m = 2 * N;
+  auto brev = [&](u64 x) {
+    u64 r = 0;
+    for (int i = 0; i < P_.logn; ++i, x >>= 1) r = (r << 1) | (x & 1);
+    return r;
+  };
+  std::vector<u32> table(N);
+  for (u64 i = 0; i < N; ++i) {
+    const u64 e = ((2 * brev(i) + 1) * elt) % m;
+    table[i] = static_cast<u32>(brev((e - 1) >> 1));
+  }
+  u32 *d = static_cast<u32 *>(dev_.dmalloc(N * sizeof(u32)));
+  dev_.h2d(d, table.data(), N * sizeof(u32));
+  dev_.sync();
+  perms_[elt] = d;
+  return d;
+}
+
+void Engine::ct_intt(u64 *ct, size_t items, int size) {
+  ntt(ct, ct, items, size * P_.L, map_mod(size * P_.L, P_.L, 0), true);
+}
+
+void Engine::multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items) {
+  Scope sc(*this);
+  const size_t ditems = pstride ? items : 1;
+  u64 *D = scratch(ditems * P_.L * P_.N);
+  lift_ntt(pt, D, ditems);
+  ntt_mac(a, D, pstride ? static_cast<size_t>(P_.L) * P_.N : 0, out, items, true);
+  ct_intt(out, items);
+}
+
+}  // namespace hhe

@@ -544,6 +544,7 @@ struct KsDigitsTmemBody {
   const u64 *reuse;  // see KsDigitsBody
   size_t reuse_stride;
   const u32 *perm;
+  int pf;  // L2 prefetch distance in items (0: off)
   static constexpr size_t smem_bytes(int nt, bool emulate) {
     return (ntt_smem_words(1 << LOGH) + 2) * 8 + (emulate ? static_cast<size_t>(2) * (1 << LOGH) * 8 : 0) + 0 * nt;
   }
@@ -553,6 +554,10 @@ struct KsDigitsTmemBody {
     const int N = 2 * S;
     const int K = C->K, L = C->L;
     const int b = bid / (2 * K), kh = bid % (2 * K), k = kh >> 1, h = kh & 1;
+    if (pf && kh == 0 && b + pf < count) {  // digits (and the reused transforms) of the item that starts two waves later
+      cta_prefetch_l2(target + static_cast<size_t>(b + pf) * stride, sizeof(u64) * L * N);
+      if (reuse) cta_prefetch_l2(reuse + static_cast<size_t>(b + pf) * reuse_stride, sizeof(u64) * L * N);
+    }
     const int gpt = G / nt;  // groups (of 8 residues) per thread; 2 slots (components) each
     double *fm = reinterpret_cast<double *>(smem);
     u32 *tslot = reinterpret_cast<u32 *>(fm + ntt_smem_words(S));
@@ -1473,6 +1478,7 @@ struct NttMacHalfBody {
   size_t sum_stride, sum_off;
   u64 *ntt_out;  // optional: NTT_i(ct) itself (canonical), same indexing as ct
   const u32 *didx;  // optional: item -> diagonal index (blocks sharing a SHAKE counter share their diagonals)
+  int pf, nl;       // L2 prefetch distance in limbs (0: off), total limbs of the launch
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
@@ -1481,6 +1487,13 @@ struct NttMacHalfBody {
     const size_t item = lb / (comps * L);
     const int cl = lb % (comps * L);
     const size_t hoff = static_cast<size_t>(h) * S;
+    if (pf && !h && lb + pf < nl) {  // operands of the CTA pair that runs two waves later: its limb, diagonal limb and running sum
+      const int lf = lb + pf;
+      const size_t itf = lf / (comps * L);
+      cta_prefetch_l2(ct + static_cast<size_t>(lf) * (2 * S), sizeof(u64) * 2 * S);
+      if (dstride) cta_prefetch_l2(D + (didx ? didx[itf] : itf) * dstride + static_cast<size_t>(lf % L) * (2 * S), sizeof(u64) * 2 * S);
+      if (!first) cta_prefetch_l2(sum + itf * sum_stride + sum_off + static_cast<size_t>(lf % (comps * L)) * (2 * S), sizeof(u64) * 2 * S);
+    }
     const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * (2 * S) + hoff;
     u64 *dst = sum + item * sum_stride + sum_off + static_cast<size_t>(cl) * (2 * S) + hoff;
     u64 *nout = ntt_out ? ntt_out + static_cast<size_t>(lb) * (2 * S) + hoff : nullptr;
@@ -1528,12 +1541,22 @@ struct Corr0MacHalfBody {
   TwRef tw;
   size_t dstride;     // L*N or 0
   const u32 *didx;    // optional: item -> diagonal index
+  int pf, nl;         // L2 prefetch distance in limbs (0: off), total limbs of the launch
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
     const int h = bid & 1, lb = bid >> 1;
     const int L = C->L, K = C->K, i = lb % L;
     const size_t item = lb / L, N = 2 * S, hoff = static_cast<size_t>(h) * S;
+    if (pf && !h && lb + pf < nl) {  // operands of the CTA pair that runs two waves later
+      const int lf = lb + pf, fi = lf % L;
+      const size_t itf = lf / L;
+      if (fi == 0) cta_prefetch_l2(acc + ((itf * 2) * K + (K - 1)) * N, sizeof(u64) * N);
+      cta_prefetch_l2(acc + ((itf * 2) * K + fi) * N, sizeof(u64) * N);
+      cta_prefetch_l2(c0_in + (itf * L + fi) * N, sizeof(u64) * N);
+      if (dstride) cta_prefetch_l2(D + (didx ? didx[itf] : itf) * dstride + static_cast<size_t>(fi) * N, sizeof(u64) * N);
+      cta_prefetch_l2(sum + (itf * 2 * L + fi) * N, sizeof(u64) * N);
+    }
     const DevMod mi = C->mod[i], msp = C->mod[K - 1];
     const u64 *sp = acc + ((item * 2) * K + (K - 1)) * N;
     double *fm = reinterpret_cast<double *>(smem);
@@ -1712,10 +1735,12 @@ struct InvClusterBody {
   Plan plan;
   const DevConsts *C;
   TwRef tw;
+  int pf, nl;  // L2 prefetch distance in limbs (0: off), total limbs of the launch
   HD void phase1(int bid, int, unsigned char *smem) const {
     constexpr int S = 1 << LOGH;
     constexpr int nt = half_threads(LOGH);
     const int h = bid & 1, lb = bid >> 1;
+    if (pf && !h && lb + pf < nl) plan.prefetch(lb + pf, C, 2 * S);
     const int tab = plan.tab(lb, C);
     const u64 *src = plan.src(lb, C, 2 * S) + static_cast<size_t>(h) * S;
     double *fm = reinterpret_cast<double *>(smem);
@@ -1776,6 +1801,7 @@ template <int LOGH>
 struct NttFwdClusterBody {
   static constexpr const char *kName = "ntt";
   static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  static constexpr bool kPeerSmem = false;  // the cluster barrier only orders the pair's global reads before the first write
   const u64 *in;
   u64 *out;
   const DevConsts *C;
@@ -1783,10 +1809,12 @@ struct NttFwdClusterBody {
   TabMap map;
   int limbs;
   size_t istride, lstride;
+  int pf, nl;  // L2 prefetch distance in limbs (0: off), total limbs of the launch
   HD size_t at(int lb) const { return static_cast<size_t>(lb / limbs) * istride + static_cast<size_t>(lb % limbs) * lstride; }
   HD void phase1(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     const int h = bid & 1, lb = bid >> 1, tab = map.id[lb % limbs];
+    if (pf && !h && lb + pf < nl) cta_prefetch_l2(in + at(lb + pf), sizeof(u64) << (LOGH + 1));
     double *fm = reinterpret_cast<double *>(smem);
     fwd_half_load_f64<LOGH>(fm, tw.fwd_f(tab), C->qf[tab], C->qinvf[tab], h, nt, RawU64{in + at(lb)});
   }
@@ -1815,6 +1843,7 @@ struct PlanScaled {  // NttBody's inverse branch: out = INTT(in) (scaled by 1/N,
   HD int tab(int lb, const DevConsts *) const { return map.id[lb % limbs]; }
   HD size_t at(int lb) const { return static_cast<size_t>(lb / limbs) * istride + static_cast<size_t>(lb % limbs) * lstride; }
   HD const u64 *src(int lb, const DevConsts *, int) const { return in + at(lb); }
+  HD void prefetch(int lb, const DevConsts *, int N) const { cta_prefetch_l2(in + at(lb), sizeof(u64) * N); }
   HD StoreScaled store(int lb, const DevConsts *C, int) const {
     const int t = tab(lb, C);
     return StoreScaled{out + at(lb), C->n_inv_f[t], C->qf[t], C->qinvf[t]};
@@ -1831,6 +1860,7 @@ struct PlanModDownGalois {  // InttModDownBody
     const size_t item = lb / C->L;
     return acc + ((item * 2 + 1) * C->K + lb % C->L) * N;
   }
+  HD void prefetch(int lb, const DevConsts *C, int N) const { cta_prefetch_l2(src(lb, C, N), sizeof(u64) * N); }
   HD StoreModDownGalois store(int lb, const DevConsts *C, int N) const {
     const int L = C->L, K = C->K, i = lb % L;
     const size_t item = lb / L, o = (item * L + i) * N;
@@ -1849,6 +1879,12 @@ struct PlanModDownAdd {  // InttModDownAddBody
     const int L = C->L;
     const size_t item = lb / (2 * L);
     return acc + ((item * 2 + ((lb / L) & 1)) * C->K + lb % L) * N;
+  }
+  HD void prefetch(int lb, const DevConsts *C, int N) const {
+    cta_prefetch_l2(src(lb, C, N), sizeof(u64) * N);
+    const int L = C->L;
+    const u64 *bs = ((lb / L) & 1) ? base1 : base0;
+    if (bs) cta_prefetch_l2(bs + static_cast<size_t>(lb / (2 * L)) * bstride + static_cast<size_t>(lb % L) * N, sizeof(u64) * N);
   }
   HD StoreModDownAdd store(int lb, const DevConsts *C, int N) const {
     const int L = C->L, K = C->K, i = lb % L, c = (lb / L) & 1;

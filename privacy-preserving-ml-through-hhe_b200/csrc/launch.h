@@ -45,16 +45,42 @@ __global__ void __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) ke
 
 // Two-CTA thread-block cluster: the bodies of a pair run phase1 on their own shared memory, meet at a cluster barrier,
 // then run phase2 with a pointer to the partner's shared memory (distributed shared memory, read-only use).
+// Barrier semantics are chosen per body (Body::kPeerSmem, default true):
+//   kPeerSmem  phase2 reads the partner's shared memory: the first barrier is a release/acquire pair (cluster.sync()); the
+//              closing barrier only keeps this CTA's shared memory alive until the partner is done with it, which needs no
+//              memory ordering: relaxed arrive (no MEMBAR.ALL.GPU + ERRBAR behind the CTA's global stores).
+//   !kPeerSmem the barrier only separates the pair's global READS (consumed into registers before the arrive) from the
+//              first global WRITE of an in-place transform: relaxed arrive, and no closing barrier at all.
+template <class B, class = void>
+struct BodyPeerSmem {
+  static constexpr bool value = true;
+};
+template <class B>
+struct BodyPeerSmem<B, decltype(void(B::kPeerSmem))> {
+  static constexpr bool value = B::kPeerSmem;
+};
+
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+
 template <class Body>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry_c2(const Body body) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry_c2(const Body body, const int strict) {
   extern __shared__ __align__(16) unsigned char hhe_smem[];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   body.phase1(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
-  cluster.sync();
+  if (BodyPeerSmem<Body>::value || strict)
+    cluster.sync();
+  else
+    cluster_sync_relaxed();
   const unsigned char *peer = cluster.map_shared_rank(hhe_smem, cluster.block_rank() ^ 1u);
   body.phase2(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem, peer);
-  cluster.sync();  // the partner may still be reading this CTA's shared memory
+  if (strict)
+    cluster.sync();
+  else if (BodyPeerSmem<Body>::value)
+    cluster_sync_relaxed();  // the partner may still be reading this CTA's shared memory
 }
 #endif
 
@@ -77,7 +103,10 @@ struct Device {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
 #endif
+  static constexpr int kMaxDevices = 64;
+  int ordinal = 0;  // CUDA device this context lives on
   int sm_count = 1;
+  bool strict_cluster = false;  // HHE_STRICT_CLUSTER=1: release/acquire cluster barriers everywhere (A/B switch)
   uint64_t launches = 0;
   bool profiling = false;
   std::vector<KernelStat> stats;
@@ -188,12 +217,13 @@ struct Device {
       cuda_check(cudaEventRecord(ev_a, stream), "cudaEventRecord");
     }
     if (smem_bytes > 48 * 1024) {
-      static size_t configured = 0;  // per Body instantiation
-      if (smem_bytes > configured) {
+      static size_t configured[kMaxDevices] = {};  // per Body instantiation and device (the attribute is per device)
+      size_t &conf = configured[ordinal & (kMaxDevices - 1)];
+      if (smem_bytes > conf) {
         cuda_check(cudaFuncSetAttribute(kernel_entry<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem_bytes)),
                    "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-        configured = smem_bytes;
+        conf = smem_bytes;
       }
     }
     kernel_entry<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
@@ -228,15 +258,16 @@ struct Device {
       cuda_check(cudaEventRecord(ev_a, stream), "cudaEventRecord");
     }
     if (smem_bytes > 48 * 1024) {
-      static size_t configured = 0;  // per Body instantiation
-      if (smem_bytes > configured) {
+      static size_t configured[kMaxDevices] = {};  // per Body instantiation and device
+      size_t &conf = configured[ordinal & (kMaxDevices - 1)];
+      if (smem_bytes > conf) {
         cuda_check(cudaFuncSetAttribute(kernel_entry_c2<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem_bytes)),
                    "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-        configured = smem_bytes;
+        conf = smem_bytes;
       }
     }
-    kernel_entry_c2<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
+    kernel_entry_c2<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body, strict_cluster ? 1 : 0);
     cuda_check(cudaGetLastError(), "cluster kernel launch");
     if (profiling) {
       cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
