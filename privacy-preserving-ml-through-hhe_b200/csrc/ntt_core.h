@@ -238,18 +238,17 @@ struct SmemIO {
   HD void group_out(int, const double *) const {}
 };
 
-template <int R, bool INVERSE, int LOGS, int S0, int LM, int MODE, class IO = SmemIO>
-HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, const IO &io = IO()) {
+// Twiddles of group g of the pass (R stages from local stage S0, transform split into 2^LM chunks): wv[(1 << d) + j] is
+// twiddle j of the pass's stage d. Separate from the butterflies so that a caller can issue these global loads one group
+// ahead of their use (FwdChainF64 / InvChainF64 device paths).
+template <int R, int LOGS, int S0, int LM>
+HD void group_tw_f64(F64Tw tw, int chunk, int g, double *wv) {
   constexpr int E = 1 << R;
-  constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
-  constexpr int G0 = S0 + LM;        // global stage of the pass
+  constexpr int LG = LOGS - S0 - R;
+  constexpr int G0 = S0 + LM;
   if (LG == 3) g = stride8_group(g);
-  const int lo = g & ((1 << LG) - 1), hi = g >> LG;
+  const int hi = g >> LG;
   const int H = (chunk << S0) + hi;  // global block index at stage G0
-  // padded shared-memory offsets: pidx(base + (e << LG)) = a0 + off(e) with compile-time off(e)
-  const int a0 = pidx(hi << (LOGS - S0)) + lo + (LG >= 4 ? (lo >> 4) : 0);
-  auto off = [](int e) constexpr { return LG >= 4 ? e * ((1 << LG) + (1 << (LG >= 4 ? LG - 4 : 0))) : (e << LG) + (e >> (LG < 4 ? 4 - LG : 0)); };
-  double wv[E];
   if (R == 3 && G0 >= 1 && (G0 % 3) == ((LOGS + LM) % 3)) {
     constexpr int kGmin = (LOGS + LM) % 3 ? (LOGS + LM) % 3 : 3;  // == tw.gmin (Engine: logn % 3, or 3), known at compile time here
     constexpr size_t kOff = f64tw_offset_c(G0, kGmin);
@@ -263,6 +262,18 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
       for (int j = 0; j < (1 << d); ++j) wv[(1 << d) + j] = tw.idx[(static_cast<size_t>(1) << (G0 + d)) + (static_cast<size_t>(H) << d) + j];
     }
   }
+}
+
+// The butterflies of group g with its twiddles in wv (see group_tw_f64).
+template <int R, bool INVERSE, int LOGS, int S0, int LM, int MODE, class IO = SmemIO>
+HD void group_core_f64(double *sm, const double *wv, double q, double qinv, int g, const IO &io = IO()) {
+  constexpr int E = 1 << R;
+  constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
+  if (LG == 3) g = stride8_group(g);
+  const int lo = g & ((1 << LG) - 1), hi = g >> LG;
+  // padded shared-memory offsets: pidx(base + (e << LG)) = a0 + off(e) with compile-time off(e)
+  const int a0 = pidx(hi << (LOGS - S0)) + lo + (LG >= 4 ? (lo >> 4) : 0);
+  auto off = [](int e) constexpr { return LG >= 4 ? e * ((1 << LG) + (1 << (LG >= 4 ? LG - 4 : 0))) : (e << LG) + (e >> (LG < 4 ? 4 - LG : 0)); };
   constexpr bool kGlobalIn = IO::kLoad && !INVERSE && S0 == 0;
   constexpr bool kGlobalOut = IO::kStore && INVERSE && S0 == 0;
   constexpr bool kGroupOut = IO::kGroupOut && !INVERSE && S0 + R == LOGS;
@@ -323,6 +334,13 @@ HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g,
   }
 }
 
+template <int R, bool INVERSE, int LOGS, int S0, int LM, int MODE, class IO = SmemIO>
+HD void group_f64(double *sm, F64Tw tw, double q, double qinv, int chunk, int g, const IO &io = IO()) {
+  double wv[1 << R];
+  group_tw_f64<R, LOGS, S0, LM>(tw, chunk, g, wv);
+  group_core_f64<R, INVERSE, LOGS, S0, LM, MODE, IO>(sm, wv, q, qinv, g, io);
+}
+
 // Synchronisation between two consecutive register passes. The groups g in [hi * 2^LGDOM, (hi + 1) * 2^LGDOM) of the
 // producing pass write exactly the residues that the same range of groups of the consuming pass reads (LGDOM = the larger
 // element-stride exponent of the two passes), and group g belongs to thread g mod NT. When the CTA size NT is known at
@@ -359,8 +377,55 @@ struct FwdChainF64 {
   static constexpr int kOut = f64_fwd_out16(B16, R, kHalfMode);
   static_assert(f64_fwd_peak16(B16, R) <= 192, "FP64 transform: intermediate bound above 12q");
   static_assert(kOut <= kLimit, "FP64 transform: pass output above the consumer's bound");
+  using Next = FwdChainF64<LOGS, LM, (kLast ? 0 : S0 + R), (kLast ? 16 : kOut), MAXOUT16, NT>;
+  static constexpr int kGroups = 1 << (LOGS - R);
+#if defined(__CUDA_ARCH__)
+  // Device path for a compile-time CTA size: the twiddles of a group are requested one group ahead of their use (the second
+  // group's while the first one computes, the next pass's first group's before the barrier that ends this pass), so their
+  // L1/L2 latency overlaps FP64 work instead of stalling the first product of every group.
+  static __device__ __forceinline__ void tw_first(F64Tw tw, int chunk, double *wv) {
+    group_tw_f64<R, LOGS, S0, LM>(tw, chunk, static_cast<int>(threadIdx.x), wv);
+  }
+  template <class IO>
+  static __device__ __forceinline__ void run_dev(double *sm, F64Tw tw, double q, double qinv, int chunk, const IO &io, double *w0) {
+    constexpr int GPT = kGroups / NT;
+    static_assert(GPT >= 1 && GPT * NT == kGroups, "pipelined passes need a whole number of groups per thread");
+    const int tid = static_cast<int>(threadIdx.x);
+    double w1[8];
+#pragma unroll
+    for (int j = 0; j < GPT; ++j) {
+      double *cur = (j & 1) ? w1 : w0, *nxt = (j & 1) ? w0 : w1;
+      if (j + 1 < GPT)
+        group_tw_f64<R, LOGS, S0, LM>(tw, chunk, tid + (j + 1) * NT, nxt);
+      else {
+        if constexpr (!kLast) Next::tw_first(tw, chunk, nxt);
+      }
+      group_core_f64<R, false, LOGS, S0, LM, kHalfMode ? kHalf : kNone, IO>(sm, cur, q, qinv, tid + j * NT, io);
+    }
+    if (kLast)
+      SYNC();
+    else
+      sync_domain<LOGS - S0 - R, NT>();
+    if constexpr (!kLast) {
+      // the next pass's first twiddles sit in the array the last group did not use
+      if constexpr (GPT & 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w0[c] = w1[c];
+      }
+      Next::run_dev(sm, tw, q, qinv, chunk, io, w0);
+    }
+  }
+#endif
   template <class IO = SmemIO>
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
+#if defined(__CUDA_ARCH__) && !defined(HHE_NO_TW_PIPELINE)
+    if constexpr (NT > 0 && kGroups % (NT > 0 ? NT : 1) == 0 && kGroups >= NT) {
+      double w0[8];
+      tw_first(tw, chunk, w0);
+      run_dev(sm, tw, q, qinv, chunk, io, w0);
+      return;
+    }
+#endif
     const int st = NT ? NT : nt;
     FOR_THREADS(tid, nt) {
 #pragma unroll
@@ -371,7 +436,7 @@ struct FwdChainF64 {
       SYNC();
     else
       sync_domain<LOGS - S0 - R, NT>();  // this pass's element stride is the larger one
-    if (!kLast) FwdChainF64<LOGS, LM, (kLast ? 0 : S0 + R), (kLast ? 16 : kOut), MAXOUT16, NT>::run(sm, tw, q, qinv, chunk, nt, io);
+    if (!kLast) Next::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
@@ -392,11 +457,55 @@ HD void ntt_fwd_core_f64_from(double *sm, F64Tw tw, double q, double qinv, int c
 // Inverse passes, highest stages first; every pass reduces on load (q/2 + 1, then three doublings: <= 4.5q).
 template <int LOGS, int LM, int S0, int NT = 0>
 struct InvChainF64 {
+  static constexpr int R0 = NttSchedule<LOGS>::kFirst;
+  static constexpr int R = S0 == 0 ? R0 : kRadixLog;
+  static constexpr int kNext = S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0;  // first stage of the pass that consumes this one
+  static constexpr int kGroups = 1 << (LOGS - R);
+  using Next = InvChainF64<LOGS, LM, kNext, NT>;
+#if defined(__CUDA_ARCH__)
+  // device path for a compile-time CTA size: twiddles requested one group ahead (see FwdChainF64::run_dev)
+  static __device__ __forceinline__ void tw_first(F64Tw tw, int chunk, double *wv) {
+    group_tw_f64<R, LOGS, S0, LM>(tw, chunk, static_cast<int>(threadIdx.x), wv);
+  }
+  template <class IO>
+  static __device__ __forceinline__ void run_dev(double *sm, F64Tw tw, double q, double qinv, int chunk, const IO &io, double *w0) {
+    constexpr int GPT = kGroups / NT;
+    static_assert(GPT >= 1 && GPT * NT == kGroups, "pipelined passes need a whole number of groups per thread");
+    const int tid = static_cast<int>(threadIdx.x);
+    double w1[8];
+#pragma unroll
+    for (int j = 0; j < GPT; ++j) {
+      double *cur = (j & 1) ? w1 : w0, *nxt = (j & 1) ? w0 : w1;
+      if (j + 1 < GPT)
+        group_tw_f64<R, LOGS, S0, LM>(tw, chunk, tid + (j + 1) * NT, nxt);
+      else {
+        if constexpr (S0 > 0) Next::tw_first(tw, chunk, nxt);
+      }
+      group_core_f64<R, true, LOGS, S0, LM, kFull, IO>(sm, cur, q, qinv, tid + j * NT, io);
+    }
+    if (S0 == 0)
+      SYNC();
+    else
+      sync_domain<LOGS - kNext - (kNext == 0 ? R0 : kRadixLog), NT>();
+    if constexpr (S0 > 0) {
+      if constexpr (GPT & 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w0[c] = w1[c];
+      }
+      Next::run_dev(sm, tw, q, qinv, chunk, io, w0);
+    }
+  }
+#endif
   template <class IO = SmemIO>
   static HD void run(double *sm, F64Tw tw, double q, double qinv, int chunk, int nt, const IO &io = IO()) {
-    constexpr int R0 = NttSchedule<LOGS>::kFirst;
-    constexpr int R = S0 == 0 ? R0 : kRadixLog;
-    constexpr int kNext = S0 - kRadixLog >= R0 ? S0 - kRadixLog : 0;  // first stage of the pass that consumes this one
+#if defined(__CUDA_ARCH__) && !defined(HHE_NO_TW_PIPELINE)
+    if constexpr (NT > 0 && kGroups % (NT > 0 ? NT : 1) == 0 && kGroups >= NT) {
+      double w0[8];
+      tw_first(tw, chunk, w0);
+      run_dev(sm, tw, q, qinv, chunk, io, w0);
+      return;
+    }
+#endif
     const int st = NT ? NT : nt;
     FOR_THREADS(tid, nt) {
 #pragma unroll
@@ -406,7 +515,7 @@ struct InvChainF64 {
       SYNC();
     else
       sync_domain<LOGS - kNext - (kNext == 0 ? R0 : kRadixLog), NT>();  // the consumer's element stride is the larger one
-    if (S0 > 0) InvChainF64<LOGS, LM, kNext, NT>::run(sm, tw, q, qinv, chunk, nt, io);
+    if (S0 > 0) Next::run(sm, tw, q, qinv, chunk, nt, io);
   }
 };
 
