@@ -28,8 +28,10 @@
  * HHE_ERR_RUNTIME to std::runtime_error / CUDA failures. There is NO CPU fallback: without a usable CUDA device
  * hhe_ctx_create fails with HHE_ERR_NO_DEVICE.
  *
- * Threading: one host thread at a time per context (each context owns one CUDA stream); contexts are independent.
- * All calls are synchronous with respect to the host unless the name ends in _async.
+ * Threading: one host thread at a time per context (each context owns its CUDA streams); contexts are independent, also
+ * across devices: every entry point makes its context's device current for the call and restores the caller's afterwards.
+ * Host-buffer calls are synchronous with respect to the host (results are in `out` on return); the hhe_dev_* calls only enqueue
+ * work on the context's stream (hhe_sync waits for it).
  */
 #ifndef HHE_B200_H
 #define HHE_B200_H
@@ -56,6 +58,9 @@ enum { HHE_KEYSET_0 = 0, HHE_KEYSET_1 = 1, HHE_RELIN = 2 };
 
 const char *hhe_last_error(void);
 const char *hhe_version(void);
+/* 1 for the product (compiled by nvcc for sm_100a). 0 only for the host emulation of the kernel bodies that the repository's
+ * CPU-tier tests build (tests/emul): bindings must refuse such a library outside those tests -- there is no CPU path. */
+int hhe_build_is_cuda(void);
 
 /* q[0..nq): coefficient-modulus primes, last = special prime (as CoeffModulus::BFVDefault returns them).
  * device: CUDA ordinal. stream: a cudaStream_t to run on (NULL: the context creates its own). */
@@ -65,7 +70,8 @@ void hhe_ctx_destroy(hhe_ctx *ctx);
  * number of moduli served by the FP64-pipe kernels (q <= 2^49; the others use the integer Shoup kernels) */
 int hhe_ctx_info(const hhe_ctx *ctx, uint64_t *info);
 void *hhe_ctx_stream(const hhe_ctx *ctx);
-/* Blocks per lock-step batch inside decompose (0 = automatic from free HBM). */
+/* Blocks per lock-step batch inside decompose. 0 = automatic: two blocks per SM, reduced if the batch's working set (about
+ * 60 MiB per block at N = 16384) would not fit 80 % of the free HBM (cudaMemGetInfo at the time of the call). */
 int hhe_set_batch(hhe_ctx *ctx, int blocks);
 uint32_t hhe_galois_elt(const hhe_ctx *ctx, int step);
 /* Constants the engine derived (for parity checks against SEAL): psi[K] then psi_t; then m_sk, gamma, m_tilde,

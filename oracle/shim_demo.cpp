@@ -87,6 +87,31 @@ int main(int argc, char **argv) {
   sealhelper_b200::encrypted_vec_sum(g_prod, g_sum, engine, sum_gk, sum_len);
   auto t2 = std::chrono::steady_clock::now();
 
+  // ---- the reference's own lines (CSP.cpp:295-298,306,311-315) with the Evaluator facade in the seal::Evaluator's place ----
+  bool facade_ok;
+  {
+    namespace sealhelper = sealhelper_b200;  // what a maintainer switches: the helper namespace and the evaluator's type
+    using Evaluator = hhe_shim::Evaluator;
+    Evaluator *csp_he_eval = new Evaluator(*context);  // CSP.cpp:19
+    auto getEvaluator = [&] { return csp_he_eval; };
+    Ciphertext tmp, tmp1;
+    sealhelper::packed_enc_multiply(g_flat, enc_w, tmp, *getEvaluator());
+    Ciphertext record = tmp;
+    getEvaluator()->relinearize_inplace(record, RelinKeys(rk));  // a temporary copy, as CSP.h:121 returns by value
+    sealhelper::encrypted_vec_sum(record, tmp1, *getEvaluator(), GaloisKeys(sum_gk), sum_len);
+    facade_ok = same(tmp, r_prod) && same(record, [&] { Ciphertext c = r_prod; eval.relinearize_inplace(c, rk); return c; }()) && same(tmp1, r_sum);
+    // a different key object at (possibly) the same address must be recognised by content: rotate with flat_gk, then sum_gk again
+    if (!flat_steps.empty()) {
+      Ciphertext a, b;
+      getEvaluator()->rotate_rows(g_flat, flat_steps[0], GaloisKeys(flat_gk), a);
+      eval.rotate_rows(r_flat, flat_steps[0], flat_gk, b);
+      facade_ok = facade_ok && same(a, b);
+      sealhelper::encrypted_vec_sum(record, tmp1, *getEvaluator(), GaloisKeys(sum_gk), sum_len);
+      facade_ok = facade_ok && same(tmp1, r_sum);
+    }
+    delete csp_he_eval;
+  }
+
   // ---- service-level calls (csp_b200::decompose / evaluate_model = BaseCSP::decompose / evaluateModel in one call each) ----
   std::vector<Ciphertext> s_flat = csp_b200::decompose(engine, {sym}, enc_key[0], flat_gk);
   std::vector<std::vector<Ciphertext>> s_res;
@@ -106,7 +131,7 @@ int main(int argc, char **argv) {
   const bool wire_ok = n_rk == 1 && n_gk == 3 && w_blocks.size() == 1 && same(w_blocks[0], r_blocks[0]);
   svc_ok = svc_ok && wire_ok;
 
-  bool ok = svc_ok && r_blocks.size() == g_blocks.size();
+  bool ok = svc_ok && facade_ok && r_blocks.size() == g_blocks.size();
   for (size_t b = 0; ok && b < r_blocks.size(); b++) ok = same(r_blocks[b], g_blocks[b]);
   ok = ok && same(r_flat, g_flat) && same(r_prod, g_prod) && same(r_sum, g_sum);
   Plaintext p;
@@ -116,8 +141,8 @@ int main(int argc, char **argv) {
   bool dec_ok = true;
   for (size_t i = 0; i < input_len; i++) dec_ok = dec_ok && slots[i] == plain[i];
   std::printf("{\"N\": %zu, \"blocks\": %zu, \"ciphertexts_identical\": %s, \"decrypts_to_plaintext\": %s, \"noise_budget\": %d, "
-              "\"serialized_keys_ok\": %s, \"reference_cpu_s\": %.3f, \"b200_s\": %.3f}\n",
-              N, blocks, ok ? "true" : "false", dec_ok ? "true" : "false", dec.invariant_noise_budget(g_sum), wire_ok ? "true" : "false",
+              "\"serialized_keys_ok\": %s, \"evaluator_facade_ok\": %s, \"reference_cpu_s\": %.3f, \"b200_s\": %.3f}\n",
+              N, blocks, ok ? "true" : "false", dec_ok ? "true" : "false", dec.invariant_noise_budget(g_sum), wire_ok ? "true" : "false", facade_ok ? "true" : "false",
               std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
   return ok && dec_ok ? 0 : 1;
 }

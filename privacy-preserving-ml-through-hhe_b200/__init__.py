@@ -32,7 +32,7 @@ SYMBOLS = [
     "hhe_dev_relinearize", "hhe_dev_multiply", "hhe_dev_pasta3_decompose", "hhe_launch_count",
     "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report", "hhe_clear_keyset",
     "hhe_seal_parms_id", "hhe_seal_ct_save_bound", "hhe_seal_ct_save", "hhe_seal_ct_load", "hhe_seal_keys_unpack",
-    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized", "hhe_pasta3_plain",
+    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized", "hhe_pasta3_plain", "hhe_build_is_cuda",
 ]
 
 
@@ -57,16 +57,23 @@ class HheNoDevice(HheError):
 _libs = {}
 
 
-def load_library(path=None):
-    """Load the shared library. Fails loudly if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+def load_library(path=None, emulation_harness=False):
+    """Load the shared library. Fails loudly if it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)
+    or if it is not the CUDA build: the host emulation of the kernel bodies (tests/emul) is accepted only when the caller says
+    it is the test harness (`emulation_harness=True`, which nothing in the package does)."""
     path = path or LIB_PATH
     if path in _libs:
-        return _libs[path]
+        l = _libs[path]
+        if not emulation_harness and not l.hhe_build_is_cuda():
+            raise HheNoDevice(HHE_ERR_NO_DEVICE, f"{path} is a host-emulation test build, not the CUDA engine: there is no CPU path")
+        return l
     if not os.path.exists(path):
         raise HheNoDevice(HHE_ERR_NO_DEVICE, f"{path} is missing: build the CUDA extension first; there is no CPU fallback")
     l = C.CDLL(path)
-    l.hhe_last_error.restype = C.c_char_p
     l.hhe_version.restype = C.c_char_p
+    if not hasattr(l, "hhe_build_is_cuda") or (not emulation_harness and not l.hhe_build_is_cuda()):
+        raise HheNoDevice(HHE_ERR_NO_DEVICE, f"{path} is not the CUDA build of the engine ({l.hhe_version().decode()}): there is no CPU path")
+    l.hhe_last_error.restype = C.c_char_p
     l.hhe_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_uint64, C.c_uint64, _u64p, C.c_int, C.c_int, C.c_void_p]
     l.hhe_ctx_destroy.argtypes = [C.c_void_p]
     l.hhe_ctx_destroy.restype = None
@@ -92,8 +99,8 @@ def _arr(a):
 class Context:
     """One engine context = one GPU, one stream, one BFV parameter set (the SEALContext + Evaluator of the reference)."""
 
-    def __init__(self, N, t, q, device=0, stream=None, lib_path=None):
-        self.lib = load_library(lib_path)
+    def __init__(self, N, t, q, device=0, stream=None, lib_path=None, emulation_harness=False):
+        self.lib = load_library(lib_path, emulation_harness)
         self.q = np.ascontiguousarray(q, dtype=np.uint64)
         self.N, self.t, self.K, self.L = int(N), int(t), len(self.q), len(self.q) - 1
         h = C.c_void_p()

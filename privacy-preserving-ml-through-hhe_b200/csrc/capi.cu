@@ -20,8 +20,27 @@ namespace {
 
 thread_local std::string g_error;
 
+// Every entry point runs with its context's device current and puts the caller's device back afterwards: contexts on
+// different GPUs may be used from one process (scratch allocations, key uploads and launches all follow the current device).
+struct DeviceScope {
+  int prev = -1;
+  ~DeviceScope() {
+#ifdef HHE_CUDA
+    if (prev >= 0) cudaSetDevice(prev);
+#endif
+  }
+};
+thread_local DeviceScope *g_scope = nullptr;
+
 template <class F>
 int guarded(F &&f) {
+  DeviceScope scope;
+  DeviceScope *outer = g_scope;
+  g_scope = &scope;
+  struct Restore {
+    DeviceScope *o;
+    ~Restore() { g_scope = o; }
+  } restore{outer};
   try {
     f();
     return HHE_OK;
@@ -39,6 +58,13 @@ int guarded(F &&f) {
 
 Engine &E(hhe_ctx *c) {
   if (!c || !c->eng) throw std::invalid_argument("null context");
+#ifdef HHE_CUDA
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur != c->eng->device()) {
+    if (g_scope && g_scope->prev < 0) g_scope->prev = cur;
+    cuda_check(cudaSetDevice(c->eng->device()), "cudaSetDevice");
+  }
+#endif
   return *c->eng;
 }
 
@@ -49,6 +75,34 @@ u64 *up(Engine &e, const u64 *host, size_t words) {
 }
 
 void down(Engine &e, u64 *host, const u64 *d, size_t words) { e.dev().d2h(host, d, words * 8); }
+
+// Results of a chunked call leave through two device buffers and the copy stream (Device::d2h_begin / d2h_end): the
+// device-to-host copy of chunk i overlaps the computation of chunk i + 1. `buf(i)` is the device buffer chunk i writes to
+// (its previous contents have been delivered), `send(i, ...)` starts the delivery, the destructor / finish() waits for all.
+struct OverlappedOut {
+  Engine &e;
+  u64 *d[2];
+  OverlappedOut(Engine &eng, size_t words_per_chunk, bool two) : e(eng) {
+    d[0] = e.scratch(words_per_chunk);
+    d[1] = two ? e.scratch(words_per_chunk) : d[0];
+  }
+  u64 *buf(size_t i) {
+    e.dev().d2h_end(static_cast<int>(i & 1));
+    return d[i & 1];
+  }
+  void send(size_t i, u64 *host, size_t words) { e.dev().d2h_begin(static_cast<int>(i & 1), host, d[i & 1], words * 8); }
+  void finish() {
+    e.dev().d2h_end(0);
+    e.dev().d2h_end(1);
+    e.dev().sync();
+  }
+  ~OverlappedOut() {
+    try {
+      finish();
+    } catch (...) {
+    }
+  }
+};
 
 // run `fn(first, n)` over [0, count) in chunks of the engine's batch limit
 template <class F>
@@ -62,7 +116,13 @@ void chunked(Engine &e, size_t count, F &&fn) {
 extern "C" {
 
 const char *hhe_last_error(void) { return g_error.c_str(); }
-const char *hhe_version(void) { return "hhe_b200 0.1 (sm_100a)"; }
+#ifdef HHE_CUDA
+const char *hhe_version(void) { return "hhe_b200 0.2 (sm_100a)"; }
+int hhe_build_is_cuda(void) { return 1; }
+#else
+const char *hhe_version(void) { return "hhe_b200 0.2 (HOST EMULATION: test harness of the kernel index arithmetic, not a product build)"; }
+int hhe_build_is_cuda(void) { return 0; }
+#endif
 
 int hhe_ctx_create(hhe_ctx **out, uint64_t N, uint64_t t, const uint64_t *q, int nq, int device, void *stream) {
   if (!out) return HHE_ERR_INVALID;
@@ -75,7 +135,12 @@ int hhe_ctx_create(hhe_ctx **out, uint64_t N, uint64_t t, const uint64_t *q, int
   });
 }
 
-void hhe_ctx_destroy(hhe_ctx *ctx) { delete ctx; }
+void hhe_ctx_destroy(hhe_ctx *ctx) {
+  guarded([&] {
+    if (ctx && ctx->eng) E(ctx);  // the engine's device current while its memory is released; the caller's restored afterwards
+    delete ctx;
+  });
+}
 
 int hhe_ctx_info(const hhe_ctx *ctx, uint64_t *info) {
   return guarded([&] {
@@ -104,7 +169,7 @@ int hhe_set_batch(hhe_ctx *ctx, int blocks) {
   return guarded([&] {
     Engine &e = E(ctx);
     if (blocks < 0) throw std::invalid_argument("batch must be >= 0");
-    e.set_batch(blocks ? blocks : 2 * e.dev().sm_count);
+    e.set_batch(blocks ? blocks : e.auto_batch());
   });
 }
 
@@ -334,19 +399,23 @@ static void decompose_host(Engine &e, const uint64_t *enc_key, const uint64_t *s
       counters[blk] = first_counter + b;
     }
   Engine::Scope sc(e);
-  const size_t ctw = e.ct_words();
+  const size_t ctw = e.ct_words(), step = static_cast<size_t>(std::max(1, e.batch_limit()));
   u64 *d_key = up(e, enc_key, ctw);
+  // all inputs go up once (128 words + a length per block); every chunk's ciphertexts come back on the copy stream while the
+  // next chunk is being transciphered
+  u64 *d_sym = up(e, sym.data(), nblocks * kPastaT);
+  u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nblocks + 1) / 2));
+  e.dev().h2d(d_lens, lens.data(), nblocks * 4);
+  OverlappedOut oo(e, std::min(step, nblocks) * ctw, nblocks > step);
+  size_t chunk = 0;
   chunked(e, nblocks, [&](size_t off, size_t nb) {
     Engine::Scope inner(e);
-    u64 *d_sym = up(e, &sym[off * kPastaT], nb * kPastaT);
-    u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nb + 1) / 2));
-    e.dev().h2d(d_lens, &lens[off], nb * 4);
-    u64 *d_out = e.scratch(nb * ctw);
+    u64 *d_out = oo.buf(chunk);
     std::vector<u64> ctr(counters.begin() + off, counters.begin() + off + nb);
-    e.pasta_decompose(d_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_out);
-    down(e, out + off * ctw, d_out, nb * ctw);
-    e.dev().sync();
+    e.pasta_decompose(d_key, d_sym + off * kPastaT, d_lens + off, ctr, nonce, use_bsgs != 0, d_out);
+    oo.send(chunk++, out + off * ctw, nb * ctw);
   });
+  oo.finish();
 }
 
 int hhe_pasta3_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words, uint64_t nonce,
@@ -383,6 +452,8 @@ int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym
     }
     // chunk over whole records so a chunk's blocks can be flattened on the device
     const size_t rec_per_chunk = std::max<size_t>(1, static_cast<size_t>(e.batch_limit()) / bpr);
+    OverlappedOut oo(e, std::min(rec_per_chunk, records) * ctw, records > rec_per_chunk);
+    size_t chunk = 0;
     for (size_t r0 = 0; r0 < records; r0 += rec_per_chunk) {
       const size_t nr = std::min(rec_per_chunk, records - r0), nb = nr * bpr;
       Engine::Scope inner(e);
@@ -398,7 +469,7 @@ int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym
       u64 *d_sym = up(e, sym.data(), nb * kPastaT);
       u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nb + 1) / 2));
       e.dev().h2d(d_lens, lens.data(), nb * 4);
-      u64 *d_blocks = e.scratch(nb * ctw), *d_flat = e.scratch(nr * ctw);
+      u64 *d_blocks = e.scratch(nb * ctw), *d_flat = oo.buf(chunk);
       e.pasta_decompose(d_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_blocks);
       if (d_ones) {  // mask the last block of every record in place
         u64 *last = e.scratch(nr * ctw), *masked = e.scratch(nr * ctw);
@@ -407,9 +478,9 @@ int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym
         e.strided_copy(masked, ctw, d_blocks + (bpr - 1) * ctw, bpr * ctw, ctw, nr);
       }
       e.flatten(d_blocks, bpr, flatten_keyset, d_flat, nr);
-      down(e, out + r0 * ctw, d_flat, nr * ctw);
-      e.dev().sync();
+      oo.send(chunk++, out + r0 * ctw, nr * ctw);
     }
+    oo.finish();
   });
 }
 
@@ -448,14 +519,17 @@ int hhe_flatten(hhe_ctx *ctx, const uint64_t *in, size_t per, int keyset, uint64
 int hhe_vec_sum(hhe_ctx *ctx, const uint64_t *a, size_t n, int keyset, uint64_t *out, size_t count) {
   return guarded([&] {
     Engine &e = E(ctx);
-    const size_t ctw = e.ct_words();
+    const size_t ctw = e.ct_words(), step = static_cast<size_t>(std::max(1, e.batch_limit()));
+    Engine::Scope outer(e);
+    OverlappedOut oo(e, std::min(step, count) * ctw, count > step);
+    size_t chunk = 0;
     chunked(e, count, [&](size_t off, size_t nb) {
       Engine::Scope sc(e);
-      u64 *da = up(e, a + off * ctw, nb * ctw), *dout = e.scratch(nb * ctw);
+      u64 *da = up(e, a + off * ctw, nb * ctw), *dout = oo.buf(chunk);
       e.vec_sum(da, n, keyset, dout, nb);
-      down(e, out + off * ctw, dout, nb * ctw);
-      e.dev().sync();
+      oo.send(chunk++, out + off * ctw, nb * ctw);
     });
+    oo.finish();
   });
 }
 
@@ -468,11 +542,13 @@ int hhe_fc_rows(hhe_ctx *ctx, const uint64_t *x, size_t samples, const uint64_t 
     u64 *dw = up(e, w, rows * ctw);
     // items are (sample, row) pairs; chunk over samples so a chunk holds whole rows-groups
     const size_t per_chunk = std::max<size_t>(1, static_cast<size_t>(e.batch_limit()) / std::max<size_t>(1, rows));
+    OverlappedOut oo(e, std::min(per_chunk, samples) * rows * ctw, samples > per_chunk);
+    size_t chunk = 0;
     for (size_t s0 = 0; s0 < samples; s0 += per_chunk) {
       const size_t ns = std::min(per_chunk, samples - s0), items = ns * rows;
       Engine::Scope inner(e);
       u64 *dx = up(e, x + s0 * ctw, ns * ctw);
-      u64 *A = e.scratch(items * ctw), *B = e.scratch(items * ctw), *t3 = e.scratch(items * e.ct_words(3));
+      u64 *A = e.scratch(items * ctw), *B = oo.buf(chunk), *t3 = e.scratch(items * e.ct_words(3));
       for (size_t s = 0; s < ns; ++s) {
         e.broadcast(dx + s * ctw, A + s * rows * ctw, ctw, rows);
         e.dev().d2d(B + s * rows * ctw, dw, rows * ctw * 8);
@@ -480,9 +556,9 @@ int hhe_fc_rows(hhe_ctx *ctx, const uint64_t *x, size_t samples, const uint64_t 
       e.multiply(A, B, t3, items);   // sealhelper::packed_enc_multiply
       e.relinearize(t3, A, items);   // Evaluator::relinearize_inplace
       e.vec_sum(A, n, keyset, B, items);  // sealhelper::encrypted_vec_sum
-      down(e, out + s0 * rows * ctw, B, items * ctw);
-      e.dev().sync();
+      oo.send(chunk++, out + s0 * rows * ctw, items * ctw);
     }
+    oo.finish();
   });
 }
 

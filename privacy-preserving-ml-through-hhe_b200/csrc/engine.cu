@@ -24,7 +24,7 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
     cuda_check(cudaStreamCreateWithFlags(&dev_.stream, cudaStreamNonBlocking), "cudaStreamCreate");
     dev_.own_stream = true;
   }
-  batch_ = 2 * dev_.sm_count;
+  batch_ = auto_batch();
 #else
   (void)stream;
   dev_.sm_count = 1;
@@ -100,9 +100,27 @@ Engine::~Engine() {
   dev_.dfree(dTw_);
   dev_.dfree(dIndex_);
   dev_.dfree(dFeistel_);
+  dev_.d2h_release();
 #ifdef HHE_CUDA
   if (dev_.own_stream) cudaStreamDestroy(dev_.stream);
 #endif
+}
+
+int Engine::auto_batch() {
+  int b = 2 * dev_.sm_count;
+#ifdef HHE_CUDA
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    // per block: BSGS keeps 16 baby rotations + 16 lifted diagonals + state/temporaries ~ 22 ciphertexts + 16 L-limb plaintexts
+    const size_t per_block = (22 * ct_words() + 16 * static_cast<size_t>(P_.L) * P_.N + 2 * static_cast<size_t>(P_.K) * P_.N) * 8;
+    size_t already = 0;
+    for (auto &c : chunks_) already += c.words * 8;  // the arena is reused
+    const size_t budget = (free_b + already) / 10 * 8;
+    const size_t fit = budget / per_block;
+    if (fit < static_cast<size_t>(b)) b = static_cast<int>(fit < 1 ? 1 : fit);
+  }
+#endif
+  return b;
 }
 
 // ------------------------------------------------------------------------------------------------ arena

@@ -26,6 +26,10 @@ class Engine {
   size_t ct_words(int size = 2) const { return static_cast<size_t>(size) * P_.L * P_.N; }
   int batch_limit() const { return batch_; }
   void set_batch(int b) { batch_ = b; }
+  int device() const { return device_; }
+  // Default lock-step batch: two blocks per SM (whole waves of the half-limb kernels), reduced so that the decomposition's
+  // working set (about 45 MiB per block at N = 16384 in BSGS mode, the larger of the two) fits the free HBM with a margin.
+  int auto_batch();
 
   // ---- scratch arena (stack discipline, stream ordered) ----
   struct Scope {

@@ -276,7 +276,7 @@ void Engine::flatten(const u64 *in, size_t per, int keyset, u64 *out, size_t ite
   const size_t ctw = ct_words();
   u64 *gath = scratch(items * ctw), *rot = scratch(items * ctw);
   for (size_t i = 0; i < per; ++i) {
-    for (size_t g = 0; g < items; ++g) dev_.d2d((i ? gath : out) + g * ctw, in + (g * per + i) * ctw, ctw * 8);
+    strided_copy(in + i * ctw, per * ctw, i ? gath : out, ctw, ctw, items);  // block i of every group in one gather launch
     if (i) {
       rotate_rows(gath, -static_cast<int>(i * kPastaT), keyset, rot, items);
       add(out, rot, out, items);

@@ -200,6 +200,82 @@ struct Device {
 #endif
   }
 
+  // ---- overlapped delivery of results to host memory (pinned-memory streaming at the boundary) ----
+  // d2h_begin(slot, ...) enqueues the copy of a finished device buffer on a SECOND stream, ordered behind everything the
+  // compute stream holds at that moment, and returns; the compute stream goes on with the next chunk. Pinned destinations
+  // (cudaHostAlloc / cudaHostRegister memory, e.g. a serving loop's ring) are written directly; pageable destinations
+  // (a std::vector, seal::Ciphertext::data()) go through one of two pinned staging buffers and are filled by d2h_end.
+  // d2h_end(slot) blocks until the data of that slot has reached its destination (and must precede reuse of the device buffer).
+#ifdef HHE_CUDA
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t produced = nullptr;
+  struct Stage {
+    void *pinned = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    void *dst = nullptr;
+    size_t bytes = 0;
+    bool pending = false, staged = false;
+  } stage[2];
+#endif
+  void d2h_begin(int slot, void *host_dst, const void *dev_src, size_t bytes) {
+#ifdef HHE_CUDA
+    d2h_end(slot);
+    Stage &st = stage[slot];
+    if (!copy_stream) {
+      cuda_check(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking), "cudaStreamCreate(copy)");
+      cuda_check(cudaEventCreateWithFlags(&produced, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    if (!st.done) cuda_check(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming), "cudaEventCreate");
+    cudaPointerAttributes attr{};
+    const bool pinned_dst = cudaPointerGetAttributes(&attr, host_dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // a pageable pointer is not an error here
+    void *target = host_dst;
+    st.staged = !pinned_dst;
+    if (st.staged) {
+      if (st.cap < bytes) {
+        if (st.pinned) cudaFreeHost(st.pinned);
+        st.pinned = nullptr, st.cap = 0;
+        cuda_check(cudaHostAlloc(&st.pinned, bytes, cudaHostAllocDefault), "cudaHostAlloc(staging)");
+        st.cap = bytes;
+      }
+      target = st.pinned;
+    }
+    cuda_check(cudaEventRecord(produced, stream), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(copy_stream, produced, 0), "cudaStreamWaitEvent");
+    cuda_check(cudaMemcpyAsync(target, dev_src, bytes, cudaMemcpyDeviceToHost, copy_stream), "cudaMemcpyAsync D2H (copy stream)");
+    cuda_check(cudaEventRecord(st.done, copy_stream), "cudaEventRecord");
+    st.dst = host_dst, st.bytes = bytes, st.pending = true;
+#else
+    (void)slot;
+    std::memcpy(host_dst, dev_src, bytes);
+#endif
+  }
+  void d2h_end(int slot) {
+#ifdef HHE_CUDA
+    Stage &st = stage[slot];
+    if (!st.pending) return;
+    cuda_check(cudaEventSynchronize(st.done), "cudaEventSynchronize(copy)");
+    if (st.staged) std::memcpy(st.dst, st.pinned, st.bytes);
+    st.pending = false;
+#else
+    (void)slot;
+#endif
+  }
+  void d2h_release() {
+#ifdef HHE_CUDA
+    for (auto &st : stage) {
+      if (st.pending) cudaEventSynchronize(st.done);
+      st.pending = false;
+      if (st.pinned) cudaFreeHost(st.pinned);
+      if (st.done) cudaEventDestroy(st.done);
+      st = Stage{};
+    }
+    if (produced) cudaEventDestroy(produced), produced = nullptr;
+    if (copy_stream) cudaStreamDestroy(copy_stream), copy_stream = nullptr;
+#endif
+  }
+
   template <class Body>
   void launch(const Body &body, size_t grid, int nt, size_t smem_bytes) {
     if (grid == 0) return;

@@ -126,14 +126,22 @@ struct Body {
   std::vector<uint8_t> own;
 };
 
-void inflate_body(const uint8_t *in, const Header &h, size_t hint, Body &b) {
+// `limit`: the largest body the encryption parameters allow for this kind of object. These streams come from other parties
+// (gRPC payloads), so the output buffer never grows beyond it: a crafted stream is rejected as invalid data instead of
+// forcing multi-GB host allocations before the member checks run.
+void inflate_body(const uint8_t *in, const Header &h, size_t hint, size_t limit, Body &b) {
   const uint8_t *src = in + kHdr;
   const size_t n = h.size - kHdr;
   if (h.compr == kComprNone) {
     b.p = src, b.n = n;
     return;
   }
-  b.own.resize(hint ? hint : 4 * n + 4096);
+  limit += 4096;  // slack: a decoder may need one more call (with room) to report the end of a body of exactly `limit` bytes
+  b.own.resize(std::min(limit, hint ? hint : 4 * n + 4096));
+  auto grow = [&] {
+    if (b.own.size() >= limit) throw std::logic_error("stream decompression failed: object larger than the encryption parameters allow");
+    b.own.resize(std::min(limit, b.own.size() * 2));
+  };
   size_t produced = 0;
   if (h.compr == kComprZlib) {
     z_stream zs{};
@@ -146,7 +154,7 @@ void inflate_body(const uint8_t *in, const Header &h, size_t hint, Body &b) {
         const size_t chunk = std::min<size_t>(n - fed, 1u << 30);
         zs.next_in = const_cast<Bytef *>(src + fed), zs.avail_in = static_cast<uInt>(chunk), fed += chunk;
       }
-      if (produced == b.own.size()) b.own.resize(b.own.size() * 2);
+      if (produced == b.own.size()) grow();
       const size_t room = std::min<size_t>(b.own.size() - produced, 1u << 30);
       zs.next_out = b.own.data() + produced, zs.avail_out = static_cast<uInt>(room);
       rc = inflate(&zs, Z_NO_FLUSH);
@@ -169,7 +177,7 @@ void inflate_body(const uint8_t *in, const Header &h, size_t hint, Body &b) {
     ZBufIn zi{src, n, 0};
     size_t rc = 1;
     while (zi.pos < zi.size || rc != 0) {
-      if (produced == b.own.size()) b.own.resize(b.own.size() * 2);
+      if (produced == b.own.size()) grow();
       ZBufOut zo{b.own.data(), b.own.size(), produced};
       rc = z.decompressStream(d, &zo, &zi);
       const bool stalled = zo.pos == produced && zi.pos == zi.size && rc != 0;
@@ -356,7 +364,8 @@ size_t ct_load(const Ring &r, const uint8_t *in, size_t len, uint64_t *ct, size_
   if (!ct || !size) throw std::invalid_argument("null buffer");
   const Header h = read_header(in, len);
   Body b;
-  inflate_body(in, h, kCtMeta + kHdr + 8 + 3 * static_cast<size_t>(r.L()) * r.N * 8, b);
+  const size_t ct_max = kCtMeta + kHdr + 8 + 3 * static_cast<size_t>(r.L()) * r.N * 8;  // a size-3 ciphertext, the largest on the path
+  inflate_body(in, h, ct_max, ct_max, b);
   Rd rd{b.p, b.n};
   int sz = 0;
   const uint8_t *data = parse_ct_members(r, rd, 0, false, &sz);
@@ -371,7 +380,10 @@ size_t ct_load(const Ring &r, const uint8_t *in, size_t len, uint64_t *ct, size_
 size_t keys_walk(const Ring &r, const uint8_t *in, size_t len, const std::function<void(uint64_t, const uint64_t *)> &on_key) {
   const Header h = read_header(in, len);
   Body b;
-  inflate_body(in, h, 0, b);
+  // one key = L PublicKey objects (size-2 ciphertexts at key level, each with its own header); at most N key slots
+  const size_t pk_max = kCtMeta + kHdr + 8 + static_cast<size_t>(2) * r.K() * r.N * 8;
+  const size_t set_max = 32 + 8 + r.N * (8 + static_cast<size_t>(r.L()) * (kHdr + pk_max));
+  inflate_body(in, h, 0, set_max, b);
   Rd rd{b.p, b.n};
   uint64_t want[4], got[4];
   parms_id(r, 1, want);
@@ -390,7 +402,7 @@ size_t keys_walk(const Ring &r, const uint8_t *in, size_t len, const std::functi
       rd.need(kHdr);
       const Header kh = read_header(rd.p + rd.o, rd.n - rd.o);
       Body kb;
-      inflate_body(rd.p + rd.o, kh, 0, kb);
+      inflate_body(rd.p + rd.o, kh, pk_max, pk_max, kb);
       Rd krd{kb.p, kb.n};
       int sz = 0;
       const uint8_t *data = parse_ct_members(r, krd, 1, true, &sz);

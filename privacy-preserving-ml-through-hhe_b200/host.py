@@ -63,6 +63,9 @@ class PASTA_SEAL:
     def flatten(self, cts, galois_keys=None):
         """SEAL_Cipher.cpp:170-181. `galois_keys` ({elt: ksk}) are uploaded as keyset 1, like the dedicated csp_gk."""
         if galois_keys:
+            # the dictionary replaces keyset 1 as a whole, like a seal::GaloisKeys object: a rotation it lacks must not find
+            # a key left over from an earlier object (SEAL would fall back to the NAF terms or throw)
+            self.ctx.clear_keyset(KEYSET_1)
             for elt, k in galois_keys.items():
                 self.ctx.load_ksk(KEYSET_1, elt, k)
             return self.ctx.flatten(cts, keys=KEYSET_1)
@@ -79,9 +82,11 @@ def encrypted_vec_sum(ctx: Context, encrypted_inp, vec_size, keyset=KEYSET_1):
     return ctx.vec_sum(encrypted_inp, vec_size, keys=keyset)
 
 
-def decompose(hhe: PASTA_SEAL, records, enc_sym_key, input_len, flatten_keys=None, mask_in_place=True):
-    """BaseCSP::decompose (CSP.cpp:235-283) for a list of symmetric-ciphertext records. `mask_in_place=False`
-    reproduces the service's mask-on-a-copy quirk; the monolithic demos mask in place."""
+def decompose(hhe: PASTA_SEAL, records, enc_sym_key, input_len, flatten_keys=None, mask_in_place=False):
+    """BaseCSP::decompose (CSP.cpp:235-283) for a list of symmetric-ciphertext records. The default, `mask_in_place=False`,
+    is the reference SERVICE's behaviour -- its mask is applied to a copy (CSP.cpp:262-269) -- and the same
+    default as hhe_csp_decompose / Context.csp_decompose (`apply_mask=0`); `True` masks in place like the monolithic demos
+    (hhe_pktnn_examples.cpp:620-624)."""
     out = []
     rem = input_len % PASTA_T
     for rec in records:

@@ -13,7 +13,9 @@
 // std::logic_error (transparent result), std::runtime_error ("too little slots for matmul implementation!", CUDA).
 #pragma once
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -47,14 +49,28 @@ class Engine {
   Engine(const Engine &) = delete;
   Engine &operator=(const Engine &) = delete;
 
+  // The engine shared by every shim object built on the same encryption parameters and device (pasta_b200::PASTA_SEAL,
+  // hhe_shim::Evaluator): keys uploaded through one of them are visible to the others, as with one seal::SEALContext.
+  static std::shared_ptr<Engine> shared(const seal::SEALContext &context, int device = 0) {
+    static std::mutex mu;
+    static std::map<std::pair<seal::parms_id_type, int>, std::weak_ptr<Engine>> registry;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(context.key_parms_id(), device);
+    if (auto e = registry[key].lock()) return e;
+    auto e = std::make_shared<Engine>(context, device);
+    registry[key] = e;
+    return e;
+  }
+
   hhe_ctx *ctx() const { return ctx_; }
   size_t ct_words(size_t size = 2) const { return size * L_ * N_; }
+  const seal::SEALContext &context() const { return context_; }
 
   // seal::KSwitchKeys (GaloisKeys / RelinKeys) -> engine keyset. ksk layout [digit][2][K][N] = back-to-back PublicKeys.
   // The object replaces whatever the keyset held before (a key it lacks is then missing, as in SEAL).
   void load(const seal::KSwitchKeys &keys, int kind) {
     check(hhe_clear_keyset(ctx_, kind));
-    loaded_[kind] = &keys;
+    has_[kind] = false;
     const auto &data = keys.data();
     for (size_t index = 0; index < data.size(); ++index) {
       if (data[index].empty()) continue;
@@ -63,19 +79,23 @@ class Engine {
       const uint32_t elt = kind == HHE_RELIN ? 0u : static_cast<uint32_t>(2 * index + 1);  // GaloisKeys::get_index inverse
       check(hhe_load_ksk(ctx_, kind, elt, flat.data()));
     }
+    fp_[kind] = fingerprint(keys);
+    has_[kind] = true;
   }
 
-  // Upload only when a different key object is asked for than the one this keyset holds (the 26-key default set is ~0.5 GB
-  // of PCIe traffic). Identity is by address: callers keep their seal::GaloisKeys alive and unmodified, as the reference does.
+  // Upload only when the keyset does not already hold these keys (the 26-key default set is ~0.5 GB of PCIe traffic).
+  // Identity is by CONTENT: the reference hands its GaloisKeys / RelinKeys around by value (CSP.h:74,121 return copies, the
+  // PASTA_SEAL ctor takes copies), so addresses say nothing -- a later temporary with other keys can sit at the same address.
+  // The fingerprint covers parms_id, which indices are present and 16 words spread over every key polynomial pair.
   void ensure_loaded(const seal::KSwitchKeys &keys, int kind) {
-    if (loaded_[kind] != &keys) load(keys, kind);
+    if (!has_[kind] || fp_[kind] != fingerprint(keys)) load(keys, kind);
   }
 
   // The same keys as they arrive over gRPC (GaloisKeys/RelinKeys::save bytes, src/examples/Analyst/Analyst.cpp:273-318): parsed by
   // the engine's SEAL wire-format codec and uploaded key by key, without materialising a seal::GaloisKeys on the host.
   size_t load_serialized(const std::string &bytes, int kind) {
     check(hhe_clear_keyset(ctx_, kind));
-    loaded_[kind] = nullptr;
+    has_[kind] = false;
     size_t n = 0;
     check(hhe_load_seal_keys(ctx_, kind, reinterpret_cast<const uint8_t *>(bytes.data()), bytes.size(), &n, nullptr));
     return n;
@@ -93,11 +113,136 @@ class Engine {
       throw std::invalid_argument("encrypted is not valid for encryption parameters");
   }
 
+  static uint64_t fingerprint(const seal::KSwitchKeys &keys) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    auto mix = [&h](uint64_t v) {
+      for (int i = 0; i < 8; ++i) {
+        h ^= (v >> (8 * i)) & 0xff;
+        h *= 0x100000001b3ULL;
+      }
+    };
+    for (uint64_t w : keys.parms_id()) mix(w);
+    const auto &data = keys.data();
+    mix(data.size());
+    for (size_t index = 0; index < data.size(); ++index) {
+      if (data[index].empty()) continue;
+      mix(index);
+      mix(data[index].size());
+      for (auto &pk : data[index]) {
+        const uint64_t *w = pk.data().data();
+        const size_t n = pk.data().dyn_array().size();
+        mix(n);
+        for (size_t s = 0; s < 16 && n; ++s) mix(w[(n - 1) * s / 15]);
+      }
+    }
+    return h;
+  }
+
  private:
-  const seal::SEALContext &context_;
+  seal::SEALContext context_;  // by value (a SEALContext is a handle on shared context data): no reference to outlive
   hhe_ctx *ctx_ = nullptr;
   size_t N_ = 0, L_ = 0;
-  const seal::KSwitchKeys *loaded_[3] = {nullptr, nullptr, nullptr};
+  uint64_t fp_[3] = {0, 0, 0};
+  bool has_[3] = {false, false, false};
+};
+
+// seal::Evaluator-shaped facade over the engine: the members the reference's path calls on its Evaluator
+// (src/examples/CSP/CSP.cpp:298,306,314; src/util/sealhelper.cpp:268-274,379-392; src/examples/hhe_pktnn_examples.cpp:653-673,
+// 957-992) with seal::Evaluator's signatures, so a call site keeps its text when the object's type is switched:
+//     Evaluator *csp_he_eval = new Evaluator(*context);                    // CSP.cpp:19, with `using hhe_shim::Evaluator;`
+//     getEvaluator()->relinearize_inplace(record, getCSPHERelinKeysMapValue(analystId));                      // CSP.cpp:306
+//     sealhelper::packed_enc_multiply(record, w, tmp, *getEvaluator());   // CSP.cpp:295-298, with sealhelper = sealhelper_b200
+// Every call runs on the GPU through the C ABI; key objects are uploaded on first use and recognised by content afterwards.
+class Evaluator {
+ public:
+  explicit Evaluator(const seal::SEALContext &context, int device = 0) : engine_(Engine::shared(context, device)) {}
+  explicit Evaluator(std::shared_ptr<Engine> engine) : engine_(std::move(engine)) {}
+  Engine &engine() const { return *engine_; }
+
+  void multiply(const seal::Ciphertext &a, const seal::Ciphertext &b, seal::Ciphertext &destination) const {
+    engine_->require_fresh_level(a, 2);
+    engine_->require_fresh_level(b, 2);
+    std::vector<uint64_t> out(engine_->ct_words(3));
+    check(hhe_multiply(engine_->ctx(), a.data(), b.data(), out.data(), 1));
+    destination = engine_->wrap(out.data(), 3);
+  }
+  void multiply_inplace(seal::Ciphertext &a, const seal::Ciphertext &b) const { multiply(a, b, a); }
+  void square(const seal::Ciphertext &a, seal::Ciphertext &destination) const { multiply(a, a, destination); }
+  void square_inplace(seal::Ciphertext &a) const { multiply(a, a, a); }
+  void relinearize(const seal::Ciphertext &a, const seal::RelinKeys &rk, seal::Ciphertext &destination) const {
+    if (a.size() == 2) {  // SEAL: nothing to do
+      destination = a;
+      return;
+    }
+    engine_->require_fresh_level(a, 3);
+    engine_->ensure_loaded(rk, HHE_RELIN);
+    std::vector<uint64_t> out(engine_->ct_words());
+    check(hhe_relinearize(engine_->ctx(), a.data(), out.data(), 1));
+    destination = engine_->wrap(out.data());
+  }
+  void relinearize_inplace(seal::Ciphertext &a, const seal::RelinKeys &rk) const { relinearize(a, rk, a); }
+  void rotate_rows(const seal::Ciphertext &a, int steps, const seal::GaloisKeys &gk, seal::Ciphertext &destination) const {
+    engine_->require_fresh_level(a, 2);
+    engine_->ensure_loaded(gk, HHE_KEYSET_1);
+    std::vector<uint64_t> out(engine_->ct_words());
+    check(hhe_rotate_rows(engine_->ctx(), a.data(), steps, HHE_KEYSET_1, out.data(), 1));
+    destination = engine_->wrap(out.data());
+  }
+  void rotate_rows_inplace(seal::Ciphertext &a, int steps, const seal::GaloisKeys &gk) const { rotate_rows(a, steps, gk, a); }
+  void rotate_columns(const seal::Ciphertext &a, const seal::GaloisKeys &gk, seal::Ciphertext &destination) const {
+    engine_->require_fresh_level(a, 2);
+    engine_->ensure_loaded(gk, HHE_KEYSET_1);
+    std::vector<uint64_t> out(engine_->ct_words());
+    check(hhe_rotate_columns(engine_->ctx(), a.data(), HHE_KEYSET_1, out.data(), 1));
+    destination = engine_->wrap(out.data());
+  }
+  void rotate_columns_inplace(seal::Ciphertext &a, const seal::GaloisKeys &gk) const { rotate_columns(a, gk, a); }
+  void add(const seal::Ciphertext &a, const seal::Ciphertext &b, seal::Ciphertext &destination) const {
+    engine_->require_fresh_level(a, 2);
+    engine_->require_fresh_level(b, 2);
+    std::vector<uint64_t> out(engine_->ct_words());
+    check(hhe_add(engine_->ctx(), a.data(), b.data(), out.data(), 1));
+    destination = engine_->wrap(out.data());
+  }
+  void add_inplace(seal::Ciphertext &a, const seal::Ciphertext &b) const { add(a, b, a); }
+  void negate_inplace(seal::Ciphertext &a) const {
+    engine_->require_fresh_level(a, 2);
+    std::vector<uint64_t> out(engine_->ct_words());
+    check(hhe_negate(engine_->ctx(), a.data(), out.data(), 1));
+    a = engine_->wrap(out.data());
+  }
+  void add_plain_inplace(seal::Ciphertext &a, const seal::Plaintext &p) const {
+    engine_->require_fresh_level(a, 2);
+    std::vector<uint64_t> pt = dense(p), out(engine_->ct_words());
+    check(hhe_add_plain(engine_->ctx(), a.data(), pt.data(), out.data(), 1));
+    a = engine_->wrap(out.data());
+  }
+  void multiply_plain(const seal::Ciphertext &a, const seal::Plaintext &p, seal::Ciphertext &destination) const {
+    engine_->require_fresh_level(a, 2);
+    std::vector<uint64_t> pt = dense(p), out(engine_->ct_words());
+    check(hhe_multiply_plain(engine_->ctx(), a.data(), pt.data(), out.data(), 1));
+    destination = engine_->wrap(out.data());
+  }
+  void multiply_plain_inplace(seal::Ciphertext &a, const seal::Plaintext &p) const { multiply_plain(a, p, a); }
+  void exponentiate_inplace(seal::Ciphertext &a, uint64_t exponent, const seal::RelinKeys &rk) const {
+    if (exponent != 3) throw std::invalid_argument("hhe_shim::Evaluator::exponentiate_inplace: only the exponent the path uses (3) is built");
+    engine_->require_fresh_level(a, 2);
+    engine_->ensure_loaded(rk, HHE_RELIN);
+    std::vector<uint64_t> out(engine_->ct_words());
+    check(hhe_exponentiate3(engine_->ctx(), a.data(), out.data(), 1));
+    a = engine_->wrap(out.data());
+  }
+
+ private:
+  // seal::Plaintext (coeff_count <= N coefficients) -> the dense u64[N] the C ABI takes
+  std::vector<uint64_t> dense(const seal::Plaintext &p) const {
+    const size_t n = engine_->context().key_context_data()->parms().poly_modulus_degree();
+    std::vector<uint64_t> pt(n, 0);
+    if (p.is_ntt_form() || p.coeff_count() > n) throw std::invalid_argument("plain is not valid for encryption parameters");
+    std::memcpy(pt.data(), p.data(), sizeof(uint64_t) * p.coeff_count());
+    return pt;
+  }
+  std::shared_ptr<Engine> engine_;
 };
 
 }  // namespace hhe_shim
@@ -109,7 +254,7 @@ class PASTA_SEAL {
  public:
   PASTA_SEAL(std::shared_ptr<seal::SEALContext> con, seal::PublicKey, seal::SecretKey, seal::RelinKeys rk, seal::GaloisKeys gk,
              int device = 0)
-      : context_(con), engine_(std::make_shared<hhe_shim::Engine>(*con, device)) {
+      : context_(con), engine_(hhe_shim::Engine::shared(*con, device)) {
     engine_->load(rk, HHE_RELIN);
     engine_->load(gk, HHE_KEYSET_0);
   }
@@ -187,6 +332,20 @@ inline void relinearize_inplace(seal::Ciphertext &encrypted, const hhe_shim::Eng
   std::vector<uint64_t> out(engine.ct_words());
   hhe_shim::check(hhe_relinearize(engine.ctx(), encrypted.data(), out.data(), 1));
   encrypted = engine.wrap(out.data());
+}
+
+inline void encrypted_vec_sum(const seal::Ciphertext &encrypted_inp, seal::Ciphertext &destination, hhe_shim::Engine &engine,
+                              const seal::GaloisKeys &gal_keys, const size_t vec_size);
+
+// The reference's own signatures (src/util/sealhelper.h:84-87,125-129) with the facade in the Evaluator's place: the call sites
+// CSP.cpp:295-298,311-315 and hhe_pktnn_examples.cpp:653-673,957-992 compile as they are written.
+inline void packed_enc_multiply(const seal::Ciphertext &encrypted1, const seal::Ciphertext &encrypted2, seal::Ciphertext &destination,
+                                const hhe_shim::Evaluator &evaluator) {
+  packed_enc_multiply(encrypted1, encrypted2, destination, static_cast<const hhe_shim::Engine &>(evaluator.engine()));
+}
+inline void encrypted_vec_sum(const seal::Ciphertext &encrypted_inp, seal::Ciphertext &destination, const hhe_shim::Evaluator &evaluator,
+                              const seal::GaloisKeys &gal_keys, const size_t vec_size) {
+  encrypted_vec_sum(encrypted_inp, destination, evaluator.engine(), gal_keys, vec_size);
 }
 
 inline void encrypted_vec_sum(const seal::Ciphertext &encrypted_inp, seal::Ciphertext &destination, hhe_shim::Engine &engine,

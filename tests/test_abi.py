@@ -63,3 +63,19 @@ def test_bad_parameters_are_invalid_argument(libpath):
         pkg.Context(1024, common.T, [15, 17])
     with pytest.raises(pkg.HheInvalidArgument):
         pkg.Context(1024, 65539, common.small_params(1024, 6))
+
+
+def test_emulation_harness_is_refused_as_a_product_library(libpath):
+    """The host emulation of the kernel bodies (tests/emul) is test infrastructure: the package refuses it unless the caller
+    states it is the harness, whether it arrives through lib_path or through HHE_B200_LIB (there is no CPU path)."""
+    emul = os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(emul)])
+    assert pkg.load_library().hhe_build_is_cuda() == 1
+    with pytest.raises(pkg.HheNoDevice):
+        pkg.load_library(emul)
+    with pytest.raises(pkg.HheNoDevice):
+        pkg.Context(1024, common.T, common.small_params(1024, 6), lib_path=emul)
+    lib = pkg.load_library(emul, emulation_harness=True)
+    assert lib.hhe_build_is_cuda() == 0 and b"EMULATION" in lib.hhe_version()
+    with pytest.raises(pkg.HheNoDevice):  # still refused afterwards (the handle is cached)
+        pkg.load_library(emul)

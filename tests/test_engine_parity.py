@@ -25,7 +25,7 @@ BSGS_STEPS = (-16, -32, -48, -64, -80, -96, -112)
 def make_ctx(backend, NN, q):
     if backend == "emul":
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(EMUL)])
-        return pkg.Context(NN, common.T, q, lib_path=EMUL)
+        return pkg.Context(NN, common.T, q, lib_path=EMUL, emulation_harness=True)
     return pkg.Context(NN, common.T, q, device=0)
 
 

@@ -20,4 +20,5 @@ def test_reference_call_sites_give_identical_ciphertexts(input_len, sum_len):
     assert out.returncode == 0, out.stdout + out.stderr
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["ciphertexts_identical"] and res["decrypts_to_plaintext"] and res["noise_budget"] > 0
+    assert res["evaluator_facade_ok"]  # the reference's own call-site lines with hhe_shim::Evaluator (keys passed as temporaries, recognised by content)
     assert res["serialized_keys_ok"]  # keys re-uploaded from their GaloisKeys::save / RelinKeys::save bytes give the same ciphertext

@@ -61,7 +61,7 @@ def test_mnist_sample_prediction(world):
     x = rng.integers(0, 256, 784, dtype=np.uint64)
     W = rng.integers(-8, 9, (10, 784))
     sym = O.pasta_plain(world["key"], T, x)
-    flat = host.decompose(hhe, [sym], [world["enc_key"]], 784)[0]
+    flat = host.decompose(hhe, [sym], [world["enc_key"]], 784, mask_in_place=True)[0]
     slots, _ = ref.decrypt(flat)
     assert np.array_equal(slots[:784], x) and not slots[784:8192].any()
     enc_w = np.stack([ref.encrypt(np.mod(W[r], T).astype(np.uint64)) for r in range(10)])

@@ -154,7 +154,7 @@ def test_invalid_streams_are_rejected_like_seal(ref, ring):
 def _ctx(backend):
     if backend == "emul":
         subprocess.check_call(["make", "-s", "-C", os.path.dirname(EMUL)])
-        return pkg.Context(N, common.T, Q, lib_path=EMUL)
+        return pkg.Context(N, common.T, Q, lib_path=EMUL, emulation_harness=True)
     return pkg.Context(N, common.T, Q, device=0)
 
 

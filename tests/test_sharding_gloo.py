@@ -19,7 +19,7 @@ pkg = common.package(); shard = importlib.import_module(common.PKG + ".shard")
 fx = np.load(os.path.join(common.ROOT, "tests", "golden", "pasta_n512.npz"))
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HHE_PORT"], rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
-ctx = pkg.Context(int(fx["N"]), int(fx["t"]), fx["q"], lib_path=os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so"))
+ctx = pkg.Context(int(fx["N"]), int(fx["t"]), fx["q"], lib_path=os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so"), emulation_harness=True)
 for name, kind in (("gk_m1", 0), ("gk_p128", 0), ("gk_col", 0), ("rk", 2)):
     ctx.load_ksk(kind, int(fx[name + "_elt"]), fx[name])
 words, first, nblk = shard.shard_stream(fx["sym_ct"], rank, world)

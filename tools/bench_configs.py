@@ -82,7 +82,7 @@ def configs123():
     host = importlib.import_module(common.PKG + ".host")
     hhe = host.PASTA_SEAL(ctx)
     def run2():
-        flat = host.decompose(hhe, [symx], [enc_key], 784)[0]
+        flat = host.decompose(hhe, [symx], [enc_key], 784, mask_in_place=True)[0]
         return flat, host.evaluate_model(ctx, [flat], enc_w, 784)[0]
     run2()
     t0 = time.perf_counter(); flat, outs = run2(); dt = time.perf_counter() - t0
