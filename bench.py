@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- PASTA-3 blocks transciphered per second at BFV N=16384, t=65537 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--blocks B] [--bsgs] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--blocks B] [--bsgs] [--stream TOTAL] [--no-configs] [--impl reference]
 
 A "step" transciphers B PASTA-3 blocks with distinct SHAKE counters per GPU (BASELINE.json configs[3], the
 SpO2-stream case, sharded: rank r, step s owns counters [(s*G + r)*B, (s*G + r + 1)*B)); work per GPU is fixed as
@@ -15,6 +15,11 @@ block over NCCL at the end of every step.
   roofline: the dominant kernel (ks_digits, the key-switch digit NTT + inner product) timed live with CUDA events.
   cpu_baseline / --impl reference: the UNMODIFIED reference (src/pasta + vendored libseal via oracle/_ref) on all host
            cores, one PASTA_SEAL per thread, one block per thread per step.
+  strong : a FIXED stream of blocks (--stream TOTAL, e.g. 65536 = BASELINE configs[3] in full; default 8 x 296) split over the
+           ranks in contiguous counter ranges: blocks/s with total work fixed, next to the weak-scaling `value`.
+  fc     : BASELINE configs[2] (ECG 128 -> 1, batch 1024) with the samples sharded over the ranks: transcipher + encrypted FC.
+  configs: (one GPU) configs 1, 2, 5 and the BSGS mode, each with a parity flag, the reference's time on this box and the
+           fraction of the HBM roofline from SURVEY.md 8(d)'s byte formulas (tools/bench_configs.py).
 """
 import argparse
 import json
@@ -136,6 +141,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-blocks-per-thread", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the secondary configs (1, 2, 3, 5, BSGS, strong-scaling sample)")
+    ap.add_argument("--stream", type=int, default=0, help="strong-scaling mode: total blocks of the fixed stream (default 8 x --blocks)")
+    ap.add_argument("--ecg-samples", type=int, default=1024)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -169,19 +177,23 @@ def main():
     B = args.blocks
 
     # ---- inputs: rank 0 generates the key material, NCCL broadcasts it (one-time, untimed) ----
+    # keyset 0: PASTA keys (+ the BSGS and flatten rotations when the secondary configs run); keyset 1: the analyst's default
+    # power-of-two Galois keys for encrypted_vec_sum (FC line); relinearisation key.
+    extras = not args.no_configs
     ref = None
-    nkeys = 4 + (7 if args.bsgs else 0)
-    key_t = torch.empty((nkeys, L, 2, L + 1, N), dtype=torch.int64, device="cuda")
-    elt_t = torch.empty((nkeys, 2), dtype=torch.int64, device="cuda")
-    ek_t = torch.empty((2, L, N), dtype=torch.int64, device="cuda")
-    sk_t = torch.empty(256, dtype=torch.int64, device="cuda")
+    steps_ = [0, -1, 128] + ([-16 * k for k in range(1, 8)] if (args.bsgs or extras) else [])
+    if extras and world == 1:
+        steps_ += [-128 * i for i in range(1, 7)]
+    meta_t = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ks = []
     if rank == 0:
-        steps_ = [0, -1, 128] + ([-16 * k for k in range(1, 8)] if args.bsgs else [])
         rng0 = np.random.default_rng(4)
         sym_key = rng0.integers(0, common.T, 256, dtype=np.uint64)
         if ref_ok:
-            ref = R.Ref(N, common.T, None, seed=4, steps=tuple(steps_), default_gk=False)
+            ref = R.Ref(N, common.T, None, seed=4, steps=tuple(steps_), default_gk=extras)
             ks = [(0, ref.galois_elt(s), ref.ksk(0, ref.galois_elt(s))) for s in steps_] + [(2, 0, ref.ksk(2))]
+            if extras:
+                ks += [(1, e, ref.ksk(1, e)) for e in ref.list_galois(1)]
             enc_key = ref.encrypt(common.pack_key(sym_key, N))
         else:
             q = common.Q_16384
@@ -192,18 +204,31 @@ def main():
                 return k
             ks = [(0, ctx.galois_elt(s), rnd_key()) for s in steps_] + [(2, 0, rnd_key())]
             enc_key = np.stack([np.stack([rng0.integers(0, m, N, dtype=np.uint64) for m in q[:L]]) for _ in range(2)])
-        for i, (kind, elt, k) in enumerate(ks):
-            key_t[i].copy_(torch.from_numpy(k.view(np.int64)))
+        meta_t[0], meta_t[1] = len(ks), int(ref is not None)
+    if world > 1:
+        dist.broadcast(meta_t, 0)
+    nkeys, have_ref = int(meta_t[0].item()), bool(meta_t[1].item())
+    extras = extras and have_ref  # the secondary configs need real keys (their parity flags decrypt with SEAL)
+    ek_t = torch.empty((2, L, N), dtype=torch.int64, device="cuda")
+    sk_t = torch.empty(256, dtype=torch.int64, device="cuda")
+    elt_t = torch.zeros((nkeys, 2), dtype=torch.int64, device="cuda")
+    if rank == 0:
+        for i, (kind, elt, _) in enumerate(ks):
             elt_t[i, 0], elt_t[i, 1] = kind, elt
         ek_t.copy_(torch.from_numpy(enc_key.view(np.int64)))
         sk_t.copy_(torch.from_numpy(sym_key.view(np.int64)))
     if world > 1:
-        for t_ in (key_t, elt_t, ek_t, sk_t):
+        for t_ in (elt_t, ek_t, sk_t):
             dist.broadcast(t_, 0)
     elts = elt_t.cpu().numpy()
-    for i in range(nkeys):
-        ctx.load_ksk(int(elts[i, 0]), int(elts[i, 1]), key_t[i].cpu().numpy().view(np.uint64))
-    del key_t
+    key_t = torch.empty((L, 2, L + 1, N), dtype=torch.int64, device="cuda")
+    for i in range(nkeys):  # one key (18 MiB) at a time: broadcast over NCCL, upload into the engine
+        if rank == 0:
+            key_t.copy_(torch.from_numpy(ks[i][2].view(np.int64)))
+        if world > 1:
+            dist.broadcast(key_t, 0)
+        ctx.load_ksk(int(elts[i, 0]), int(elts[i, 1]), key_t.cpu().numpy().view(np.uint64))
+    del key_t, ks
     enc_key = ek_t.cpu().numpy().view(np.uint64)
     sym_key = sk_t.cpu().numpy().view(np.uint64)
 
@@ -323,6 +348,95 @@ def main():
             res[name] = {"GBps": limbs * 16 * N / t / 1e6, "limb_transforms_per_s": limbs / t * 1e3, "frac_of_hbm_peak": limbs * 16 * N / t / 1e6 / peak_hbm()[0]}
         ntt_info = {"limbs_per_launch": limbs, "bytes_per_limb": 16 * N, "fwd": res["fwd"], "inv": res["inv"],
                     "note": "exact 49-bit modular transforms on the FP64 pipe (7 FP64 + 1 FRND per butterfly): pipe ceiling = 23 M limbs/s = 6.1 TB/s equivalent"}
+    # ---- sharding invariance on the hardware: the digests rank 0 gathered in the last timed step came from
+    # every rank's own GPU; rank 0 now transciphers the first blocks of every OTHER rank's shard itself (same counters, same words,
+    # regenerated from that rank's seed) and the 64-bit digests must agree: a block's ciphertext depends on (counter, words) only ----
+    invariance = None
+    if world > 1:
+        device_step(args.warmup + args.steps - 1)  # digests of a known step (the e2e loop reused d_out)
+        barrier()
+        if rank == 0:
+            per = 2
+            last = args.warmup + args.steps - 1
+            ctrs, words = [], []
+            for r in range(1, world):
+                base = (last * world + r) * B
+                ctrs += list(range(base, base + per))
+                words.append(np.random.default_rng(1000 + r).integers(0, common.T, (B, 128), dtype=np.uint64)[:per])
+            words = np.concatenate(words)
+            d_w = torch.from_numpy(words.view(np.int64)).cuda()
+            d_o = torch.empty((len(ctrs), 2, L, N), dtype=torch.int64, device="cuda")
+            ctx.dev_pasta3_decompose(ptr(ek_t), ptr(d_w), np.full(len(ctrs), 128, dtype=np.uint32), np.array(ctrs, dtype=np.uint64),
+                                     common.NONCE, args.bsgs, ptr(d_o))
+            ctx.sync()
+            mine = d_o.view(len(ctrs), -1).sum(dim=1).view(world - 1, per)
+            theirs = digests[1:, :per]
+            invariance = {"ranks_checked": world - 1, "blocks_per_rank": per, "digests_match": bool(torch.equal(mine, theirs)),
+                          "what": "rank 0 re-transciphered blocks of every other rank's shard; 64-bit digests over all limbs compared"}
+            del d_o, d_w
+        barrier()
+
+    # ---- strong scaling: a FIXED stream of blocks split over the ranks (BASELINE configs[3]: 65,536 blocks = --stream 65536) ----
+    strong = None
+    if not args.no_configs or args.stream:
+        total = args.stream if args.stream else 8 * B
+        per_rank = (total + world - 1) // world
+        lo, hi = min(total, rank * per_rank), min(total, (rank + 1) * per_rank)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for off in range(lo, hi, B):
+            nb = min(B, hi - off)
+            ctx.dev_pasta3_decompose(ptr(d_key), ptr(d_sym), lens[:nb], np.arange(off, off + nb, dtype=np.uint64), common.NONCE, args.bsgs,
+                                     ptr(d_out))
+        s1.record(stream)
+        barrier()
+        st_ms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(st_ms, op=dist.ReduceOp.MAX)
+        strong = {"scaling": "strong", "total_blocks": total, "blocks_per_rank": per_rank, "ms": float(st_ms.item()),
+                  "value": total / float(st_ms.item()) * 1e3, "unit": UNIT,
+                  "note": "contiguous counter ranges per rank, no data-path collective; BASELINE configs[3] in full is --stream 65536"}
+
+    # ---- FC line: BASELINE configs[2] (ECG 128 -> 1, batch of 1024 one-block records that all restart at counter 0), samples sharded
+    # over the ranks; per sample: transcipher, packed_enc_multiply, relinearize, encrypted_vec_sum(128) with the default Galois keys ----
+    fc = None
+    if extras:
+        from tools import bench_configs as BC
+        rngf = np.random.default_rng(33)
+        S_all = args.ecg_samples - args.ecg_samples % world
+        xs_all = rngf.integers(0, 256, (S_all, 128), dtype=np.uint64)
+        wts = rngf.integers(-128, 128, 128)
+        S = S_all // world
+        xs = xs_all[rank * S:(rank + 1) * S]
+        from oracle import oracle as O
+        syms = np.stack([O.pasta_plain(sym_key, common.T, xs[i]) for i in range(S)])
+        w_t = torch.empty((1, 2, L, N), dtype=torch.int64, device="cuda")
+        if rank == 0:
+            w_t.copy_(torch.from_numpy(ref.encrypt(np.mod(wts, common.T).astype(np.uint64)).view(np.int64)[None]))
+        if world > 1:
+            dist.broadcast(w_t, 0)
+        enc_w1 = w_t.cpu().numpy().view(np.uint64)
+        ctx.set_batch(0)
+        BC.config3_run(ctx, enc_key, syms[:min(S, 8)], enc_w1)  # warm-up (arena, key paths)
+        barrier()
+        outs, dt = BC.config3_run(ctx, enc_key, syms, enc_w1)
+        barrier()
+        t_f = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_f, op=dist.ReduceOp.MAX)
+        ok = None
+        if rank == 0:
+            ok = all(int(ref.decrypt(outs[i, 0])[0][127]) == int(np.dot(xs[i].astype(np.int64), wts)) % common.T for i in (0, S // 2, S - 1))
+            nbytes = BYTES_PER_BLOCK[False] + BC.fc_row_bytes(128)
+            fc = {"workload": "BASELINE configs[2]: ECG 128->1, samples sharded over the ranks, host buffers in and out", "samples": S_all,
+                  "samples_per_rank": S, "s": float(t_f.item()), "value": S_all / float(t_f.item()), "unit": "samples/s",
+                  "parity_decrypted_dot_products": bool(ok),
+                  "parity_note": "FC row limb-exact vs the reference: tests/test_gpu_fc.py::test_ecg_row_bit_exact_with_seal",
+                  "algorithmic_bytes_per_sample": nbytes, "frac_of_hbm_roofline": nbytes * S_all / world / float(t_f.item()) / 1e9 / peak_hbm()[0]}
+        ctx.set_batch(args.blocks)
+        del outs
+
     # ---- the final gather of the result ciphertexts themselves to rank 0 over NCCL/NVLink, outside the timed steps:
     # the steps gather digests only (65,536 result ciphertexts are 128 GiB); a caller that wants the ciphertexts pays this once ----
     gather_info = None
@@ -348,35 +462,53 @@ def main():
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
+    # ks_digits is NOT HBM-bound: it is bound by the FP64 pipe (exact 49-bit modular products are 5 FP64 + 1 FRND instructions) with
+    # the L2->SM path as co-limiter (profiles/r2_ksdigits_ncu.txt). The headline fraction is therefore the FP64-pipe one; the HBM view
+    # (SURVEY.md 8(d)'s algorithmic bytes: one key switch = 2 ciphertexts = 4 MiB per item) is reported beside it.
     peak, peak_src = peak_hbm()
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     ks = prof.get("ks_digits", {"launches": 0, "ms": 0.0})
     avg_ms = ks["ms"] / max(1, ks["launches"])
-    achieved = KS_BYTES * B / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
-    traffic, ncu = None, None
+    hbm_achieved = KS_BYTES * B / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    ncu = None
     tpath = os.path.join(ROOT, "profiles", "ks_digits_traffic.json")
     if os.path.exists(tpath):
         ncu = json.load(open(tpath))
-        # the capture ran at 148 items per launch; DRAM traffic scales with the items of a launch
-        traffic = int(ncu["dram_bytes_per_launch_at_capture_batch_148"] * B / 148)
+    cap_items = (ncu or {}).get("capture_items", 148)
+    if ncu and "dram_bytes_per_launch" not in ncu and "dram_bytes_per_launch_at_capture_batch_148" in ncu:  # round-1 file layout
+        ncu["dram_bytes_per_launch"] = ncu["dram_bytes_per_launch_at_capture_batch_148"]
+    # the capture ran at `capture_items` items per launch; DRAM traffic scales with the items of a launch
+    traffic = int(ncu["dram_bytes_per_launch"] * B / cap_items) if ncu and "dram_bytes_per_launch" in ncu else None
+    # FP64 warp instructions per item: counted by ncu (smsp__inst_executed_pipe_fp64.sum of the captured launch / its items) when the
+    # capture carries it, otherwise the count derived from the kernel's pass structure (they agree within 2 %)
+    fp64_warp_per_item = (ncu or {}).get("fp64_warp_inst_per_item") or KS_FP64_PER_ITEM / 32.0
+    fp64_src = "ncu smsp__inst_executed_pipe_fp64.sum (profiles/ks_digits_traffic.json)" if (ncu or {}).get("fp64_warp_inst_per_item") \
+        else "derived from the kernel's pass structure"
     kernel_ms = sum(v["ms"] for v in prof.values())
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp64_peak = 148 * FP64_LANES_PER_SM_CLK * sm_mhz * 1e6
-    fp64_ach = KS_FP64_PER_ITEM * B / (avg_ms * 1e-3) if avg_ms else 0.0
+    fp64_peak = 148 * 4 * 0.5 * sm_mhz * 1e6  # warp instructions/s: one per 2 cycles per SM sub-partition (tools/microbench/pipes.cu)
+    fp64_ach = fp64_warp_per_item * B / (avg_ms * 1e-3) if avg_ms else 0.0
     roofline = {
-        "bound": "hbm", "kernel": "ks_digits (key-switch digit NTT + key inner product)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": KS_BYTES * B, "avg_launch_ms": avg_ms, "launches": ks["launches"],
+        "bound": "fp64_pipe", "kernel": "ks_digits (key-switch digit NTT + key inner product)",
+        "achieved": fp64_ach / 1e12, "peak": fp64_peak / 1e12, "unit": "T warp-inst/s (FP64 pipe)", "frac": fp64_ach / fp64_peak if avg_ms else None,
+        "traffic": traffic, "peak_source": "148 SMs x 4 sub-partitions x 1 FP64 warp instruction per 2 cycles x the SM clock sampled during the run "
+                                           "(microbench: profiles/r1_pipes_microbench.txt)",
+        "fp64_warp_inst_per_item": fp64_warp_per_item, "fp64_count_source": fp64_src,
+        "avg_launch_ms": avg_ms, "launches": ks["launches"], "items_per_launch": B,
         "share_of_kernel_time": ks["ms"] / kernel_ms if kernel_ms else None, "dominant_by_time": dom[0],
-        "ncu": ({k: ncu[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "lsu_wavefront_pipe_pct", "dram_throughput_pct", "source")}
+        "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "traffic": traffic,
+                "algorithmic_bytes_per_launch": KS_BYTES * B, "peak_source": peak_src,
+                "note": "algorithmic bytes (one key switch = 2 ciphertexts per item) over the live launch time: small by construction, the "
+                        "kernel's operands are L2-resident"},
+        "l2_to_sm": ({"bytes_per_launch": int(ncu["l2_to_sm_bytes_per_launch"] * B / cap_items),
+                      "GBps": ncu["l2_to_sm_bytes_per_launch"] * B / cap_items / (avg_ms * 1e-3) / 1e9 if avg_ms else None,
+                      "note": "every CTA streams its digits (128 KiB), key slice (128 KiB) and last-pass twiddles (56 KiB) per digit from the L2: "
+                              "the second limiter next to the FP64 pipe"} if ncu and "l2_to_sm_bytes_per_launch" in ncu else None),
+        "ncu": ({k: ncu[k] for k in ("fp64_pipe_active_pct", "issue_active_pct", "lsu_wavefront_pipe_pct", "dram_throughput_pct", "source") if k in ncu}
                 if ncu else None),
-        "note": "exact 64-bit modular arithmetic on the FP64 pipe: bounded by that pipe / the LSU data pipe, not HBM (see DESIGN.md, profiles/)",
-        "fp64_pipe": {"algorithmic_instr_per_item": KS_FP64_PER_ITEM, "achieved_tera_instr_per_s": fp64_ach / 1e12,
-                      "peak_tera_instr_per_s": fp64_peak / 1e12, "frac": fp64_ach / fp64_peak if avg_ms else None,
-                      "peak_source": "148 SMs x 64 FP64 lanes/clk x SM clock sampled during the run (microbench: profiles/r1_pipes_microbench.txt)"},
         "step_level": {"algorithmic_bytes_per_block": BYTES_PER_BLOCK[bool(args.bsgs)],
                        "achieved": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9,
-                       "frac": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9 / peak},
+                       "frac": BYTES_PER_BLOCK[bool(args.bsgs)] * value / world / 1e9 / peak, "unit": "GB/s", "peak": peak},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
     }
     # ---- CPU baseline: the reference itself on this box's host cores (bounded sample) ----
@@ -385,11 +517,50 @@ def main():
         cores = os.cpu_count() or 1
         if ref is not None:
             secs = ref.bench_decompose(enc_key, cores, 1, args.bsgs)
-            cpu = {"value": cores / secs, "unit": UNIT, "cores": cores, "kind": "reference",
+            cpu = {"value": cores / secs, "unit": UNIT, "cores": cores, "kind": "reference", "sample_s": secs,
                    "sample": f"{cores} threads x 1 block, one pasta::PASTA_SEAL per thread (reference sources + libseal-4.0.a), {secs:.1f} s"}
         else:
             from oracle import oracle as O
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "oracle/_ref absent; run tests for the port"}
+    # ---- secondary configs (one GPU): 1, 2, 5 and the BSGS mode (config 3 is the `fc` line above, config 4 the headline) ----
+    configs = None
+    if extras and world == 1:
+        from tools import bench_configs as BC
+        rngc = np.random.default_rng(8)
+        ctx.set_batch(0)
+        blk_s = cpu["sample_s"] if cpu and cpu.get("sample_s") else ref.bench_decompose(enc_key, 1, 1, False)
+        ref_ops = {"block_s": blk_s, "rotate_s": ref.bench_primitive(enc_key, 2, 3), "relinearize_s": ref.bench_primitive(enc_key, 3, 2),
+                   "multiply_plain_s": ref.bench_primitive(enc_key, 4, 2), "multiply_s": ref.bench_primitive(enc_key, 5, 2)}
+        configs = {"reference_ops_1core_s": ref_ops, "config1_one_block": BC.config1(ctx, ref, enc_key, sym_key, rngc, peak)}
+        # BSGS mode on the headline batch, device resident
+        ctx.set_batch(args.blocks)
+        from oracle import oracle as O
+        for _ in range(2):
+            ctx.dev_pasta3_decompose(ptr(d_key), ptr(d_sym), lens, counters(0), common.NONCE, True, ptr(d_out))
+        ctx.sync()
+        got0 = d_out[0].cpu().numpy().view(np.uint64)  # counter 0 (one GPU): must decrypt to the PASTA plaintext of block 0's words
+        dec_ok = bool(np.array_equal(ref.decrypt(got0)[0][:128], O.pasta_plain(sym_key, common.T, sym_np[0], decrypt=True)))
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for s_ in range(2):
+            ctx.dev_pasta3_decompose(ptr(d_key), ptr(d_sym), lens, counters(1 + s_), common.NONCE, True, ptr(d_out))
+        b1.record(stream)
+        ctx.sync()
+        bs = b0.elapsed_time(b1) * 1e-3 / 2
+        configs["bsgs_mode"] = {"blocks_per_s": B / bs, "ms_per_step": bs * 1e3, "blocks": B, "parity_note": "limb-exact vs the reference with "
+                                "use_bsgs=true: config1_one_block.bsgs here and tests/test_gpu_fullsize.py::test_bsgs_block_bit_exact_with_seal",
+                                "block_decrypts": dec_ok, "algorithmic_bytes_per_block": BYTES_PER_BLOCK[True],
+                                "frac_of_hbm_roofline": BYTES_PER_BLOCK[True] * B / bs / 1e9 / peak}
+        ctx.set_batch(0)
+        configs["config2_mnist_sample"] = BC.config2(ctx, ref, enc_key, sym_key, rngc, peak, ref_ops)
+        if fc:
+            per_sample = ref_ops["block_s"] + ref_ops["multiply_s"] + ref_ops["relinearize_s"] + BC.KS_COUNT[128] * ref_ops["rotate_s"]
+            fc["reference_1core_s_per_sample"] = per_sample
+            fc["reference_kind"] = "composed from the reference's per-operation times measured in this run (block + multiply + relinearize + 355 key switches)"
+            fc["speedup_vs_1core"] = fc["value"] * per_sample
+        ctx.close()
+        fac = lambda n_: R.Ref(n_, common.T, None, seed=5, steps=(0, -1), default_gk=False)  # noqa: E731
+        configs["config5_primitive_sweep"] = BC.config5(stream, peak, fac)
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -400,6 +571,7 @@ def main():
                         "inside); `value`'s timed region additionally records two CUDA events per kernel launch for the live per-kernel "
                         "table (about 1 %), which is why e2e can come out marginally above it"},
         "gpu_launches": int(launches), "clocks": clocks, "verified": checked, "ntt": ntt_info, "gather": gather_info,
+        "sharding_invariance": invariance, "strong": strong, "fc": fc, "configs": configs,
     }
     emit(out)
 

@@ -99,7 +99,9 @@ int main(int argc, char **argv) {
     Ciphertext record = tmp;
     getEvaluator()->relinearize_inplace(record, RelinKeys(rk));  // a temporary copy, as CSP.h:121 returns by value
     sealhelper::encrypted_vec_sum(record, tmp1, *getEvaluator(), GaloisKeys(sum_gk), sum_len);
-    facade_ok = same(tmp, r_prod) && same(record, [&] { Ciphertext c = r_prod; eval.relinearize_inplace(c, rk); return c; }()) && same(tmp1, r_sum);
+    Ciphertext r_prod3;  // the reference's size-3 product (r_prod was relinearized in place above)
+    ::sealhelper::packed_enc_multiply(r_flat, enc_w, r_prod3, eval);
+    facade_ok = same(tmp, r_prod3) && same(record, r_prod) && same(tmp1, r_sum);
     // a different key object at (possibly) the same address must be recognised by content: rotate with flat_gk, then sum_gk again
     if (!flat_steps.empty()) {
       Ciphertext a, b;

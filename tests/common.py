@@ -78,3 +78,64 @@ def load_keys_from_ref(dst, ref, keysets=(0, 1)):
         for elt in ref.list_galois(kind):
             dst.load_ksk(kind, elt, ref.ksk(kind, elt))
     dst.load_ksk(2, 0, ref.ksk(2))
+
+
+# ---- a self-contained key generator for the test ring (keys are inputs; any valid RLWE key set will do) -------------
+class ToyKeys:
+    """Secret key + key-switching keys built with the oracle's NTT (symmetric-key RLWE, SEAL's key layout)."""
+
+    def __init__(self, orc, seed):
+        self.o, self.rng = orc, np.random.default_rng(seed)
+        self.N, self.K, self.L, self.q = orc.N, orc.K, orc.L, [int(v) for v in orc.q]
+        s = self.rng.integers(-1, 2, self.N)
+        self.s_ntt = np.stack([orc.ntt(k, np.mod(s, self.q[k]).astype(np.uint64)) for k in range(self.K)])
+
+    def _mul(self, a, b, k):
+        return np.array([int(x) * int(y) % self.q[k] for x, y in zip(a, b)], dtype=np.uint64)
+
+    def ksk(self, new_key_ntt):
+        """key[J][c][k]: c0 = -(a s + e) + q_sp * new_key [only on limb J], c1 = a  (all NTT form)"""
+        out = np.zeros((self.L, 2, self.K, self.N), dtype=np.uint64)
+        qsp = self.q[-1]
+        for J in range(self.L):
+            e = self.rng.integers(-3, 4, self.N)
+            for k in range(self.K):
+                qk = self.q[k]
+                a = self.rng.integers(0, qk, self.N, dtype=np.uint64)
+                e_ntt = self.o.ntt(k, np.mod(e, qk).astype(np.uint64))
+                c0 = (qk - (self._mul(a, self.s_ntt[k], k).astype(object) + e_ntt.astype(object)) % qk) % qk
+                if k == J:
+                    c0 = (c0 + (qsp % qk) * new_key_ntt[k].astype(object)) % qk
+                out[J, 0, k] = np.array(c0, dtype=np.uint64)
+                out[J, 1, k] = a
+        return out
+
+    def galois_key(self, elt):
+        # s(X^elt) in NTT form: permute coefficient form then transform
+        s_coeff = [self.o.ntt(k, self.s_ntt[k], inverse=True) for k in range(self.K)]
+        g = np.zeros((self.K, self.N), dtype=np.uint64)
+        for k in range(self.K):
+            idx = (np.arange(self.N, dtype=np.int64) * elt) % (2 * self.N)
+            val = s_coeff[k].copy()
+            neg = idx >= self.N
+            val[neg] = (self.q[k] - val[neg]) % self.q[k]
+            tmp = np.zeros(self.N, dtype=np.uint64)
+            tmp[idx % self.N] = val
+            g[k] = self.o.ntt(k, tmp)
+        return self.ksk(g)
+
+    def relin_key(self):
+        s2 = np.stack([self._mul(self.s_ntt[k], self.s_ntt[k], k) for k in range(self.K)])
+        return self.ksk(s2)
+
+    def encrypt_zero_plus(self, orc, pt):
+        """(c0, c1) = (-(a s + e) , a) + Delta*pt on c0 -- a valid fresh BFV ciphertext of pt."""
+        ct = np.zeros((2, self.L, self.N), dtype=np.uint64)
+        e = self.rng.integers(-3, 4, self.N)
+        for i in range(self.L):
+            qi = self.q[i]
+            a = self.rng.integers(0, qi, self.N, dtype=np.uint64)
+            as_ = orc.ntt(i, self._mul(orc.ntt(i, a), self.s_ntt[i], i), inverse=True)
+            ct[0, i] = np.array((qi - (as_.astype(object) + np.mod(e, qi).astype(object)) % qi) % qi, dtype=np.uint64)
+            ct[1, i] = a
+        return orc.add_plain(ct, pt)

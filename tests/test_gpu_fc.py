@@ -82,3 +82,42 @@ def test_missing_default_key_raises_like_seal(world):
     c = world["enc_key"]
     with pytest.raises(pkg.HheInvalidArgument):
         ctx.vec_sum(c, 5, keys=0)  # keyset 0 has no power-of-two keys: NAF(-2) = single term without a key
+
+
+def test_mnist_output_neuron_limb_exact(world):
+    """ONE output neuron of the 784 -> 10 layer, every limb of the result ciphertext equal to
+    the reference's own op sequence -- multiply, relinearize, encrypted_vec_sum(784): 783 rotations from the same input,
+    2,875 key switches of SEAL's NAF chains (sealhelper.cpp:379-392), about 100 s of SEAL on one host core."""
+    ref, ctx, rng = world["ref"], world["ctx"], world["rng"]
+    x = np.zeros(N // 2, dtype=np.uint64)
+    x[:784] = rng.integers(0, 256, 784, dtype=np.uint64)
+    w = rng.integers(-8, 9, 784)
+    cx, cw = ref.encrypt(x), ref.encrypt(np.mod(w, T).astype(np.uint64))
+    lin = ctx.relinearize(ctx.multiply(cx, cw))
+    assert np.array_equal(lin, ref.relinearize(ref.multiply(cx, cw)))
+    got = ctx.vec_sum(lin, 784)
+    assert np.array_equal(got, ref.vec_sum(lin, 784, 1))
+    slots, budget = ref.decrypt(got)
+    assert budget > 0 and signed(slots[783]) == int(np.dot(x[:784].astype(np.int64), w))
+
+
+def test_siesta_record_flattened_limb_exact(world):
+    """A 300-word record (the service's inputLen, CSPRPC.cpp:196): 3 blocks -> mask of the last block (44 ones) -> flatten with the
+    dedicated keys for -128 and -256, both the demo behaviour (mask in place) and the service's (mask on a copy), every limb
+    against the reference's PASTA_SEAL::decomposition / mask / flatten (SEAL_Cipher.cpp:161-181)."""
+    ref, ctx, hhe, rng = world["ref"], world["ctx"], world["hhe"], world["rng"]
+    rec = rng.integers(0, 32, 300, dtype=np.uint64)
+    sym = O.pasta_plain(world["key"], T, rec)
+    want_blocks = ref.pasta_decompose(world["enc_key"], sym)
+    got_blocks = hhe.decomposition(sym, [world["enc_key"]], True)
+    assert np.array_equal(got_blocks, want_blocks)
+    ones = np.ones(300 % 128, dtype=np.uint64)
+    masked = [want_blocks[0], want_blocks[1], ref.mask(want_blocks[2], ones)]
+    want_demo, want_service = ref.flatten(np.stack(masked), 0), ref.flatten(want_blocks, 0)
+    assert np.array_equal(host.decompose(hhe, [sym], [world["enc_key"]], 300, mask_in_place=True)[0], want_demo)
+    assert np.array_equal(host.decompose(hhe, [sym], [world["enc_key"]], 300)[0], want_service)
+    # the one-call service entry point, both mask modes (keyset 0 holds the -128 i keys in this fixture)
+    assert np.array_equal(ctx.csp_decompose(world["enc_key"], sym, records=1, apply_mask=True, flatten_keys=0)[0], want_demo)
+    assert np.array_equal(ctx.csp_decompose(world["enc_key"], sym, records=1, apply_mask=False, flatten_keys=0)[0], want_service)
+    slots, _ = ref.decrypt(want_demo)
+    assert np.array_equal(slots[:300], rec) and not slots[300:8192].any()

@@ -192,3 +192,46 @@ def test_n8192_primitives_bit_exact_with_seal():
     assert np.array_equal(ctx.pasta3_decompose(ek, sym), ref.pasta_decompose(ek, sym, False))
     ctx.close()
     ref.close()
+
+
+@pytest.fixture(scope="module")
+def world_bsgs():
+    """Keys for the baby-step/giant-step affine layer: rotations by -16 k, k = 1..7 (pasta_3_seal.cpp:190-201)."""
+    steps = (0, -1, 128) + tuple(-16 * k for k in range(1, 8))
+    ref = R.Ref(N, common.T, None, seed=13, steps=steps, default_gk=False)
+    ctx = pkg.Context(N, common.T, ref.q, device=0)
+    common.load_keys_from_ref(ctx, ref, keysets=(0,))
+    rng = np.random.default_rng(17)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    yield dict(ref=ref, ctx=ctx, rng=rng, key=key, enc_key=ref.encrypt(common.pack_key(key, N)))
+    ctx.close()
+    ref.close()
+
+
+def test_bsgs_block_bit_exact_with_seal(world_bsgs):
+    """PASTA_SEAL::babystep_giantstep (pasta_3_seal.cpp:267-366, N1 = 16, N2 = 8) at the real size: the FP64 inner-sum kernel,
+    the pre-rotated diagonals and the -16 k keys, every limb against the reference run with use_bsgs = true (13 s of SEAL)."""
+    ref, ctx, rng, key = world_bsgs["ref"], world_bsgs["ctx"], world_bsgs["rng"], world_bsgs["key"]
+    pt = rng.integers(0, common.T, 128, dtype=np.uint64)
+    sym = O.pasta_plain(key, common.T, pt)
+    want = ref.pasta_decompose(world_bsgs["enc_key"], sym, use_bsgs=True)
+    got = ctx.pasta3_decompose(world_bsgs["enc_key"], sym, use_bsgs=True)
+    assert np.array_equal(got, want)
+    slots, budget = ref.decrypt(got[0])
+    assert budget > 60 and np.array_equal(slots[:128], pt)
+    # the two affine-layer modes are different op sequences: same plaintext, different ciphertexts
+    diag = ctx.pasta3_decompose(world_bsgs["enc_key"], sym, use_bsgs=False)
+    assert not np.array_equal(diag, got) and np.array_equal(ref.decrypt(diag[0])[0][:128], pt)
+
+
+def test_bsgs_batch_matches_single_calls(world_bsgs):
+    """BSGS mode, batched: distinct counters and records sharing counter 0 give the ciphertexts of one-block calls."""
+    ref, ctx, rng, key = world_bsgs["ref"], world_bsgs["ctx"], world_bsgs["rng"], world_bsgs["key"]
+    pt = rng.integers(0, common.T, 3 * 128, dtype=np.uint64)
+    sym = O.pasta_plain(key, common.T, pt)
+    full = ctx.pasta3_decompose(world_bsgs["enc_key"], sym, use_bsgs=True)
+    one = ctx.pasta3_decompose(world_bsgs["enc_key"], sym[256:384], use_bsgs=True, first_counter=2)
+    assert np.array_equal(one[0], full[2])
+    assert np.array_equal(ref.decrypt(full[1])[0][:128], pt[128:256])
+    recs = ctx.pasta3_decompose(world_bsgs["enc_key"], np.concatenate([sym[:128], sym[:128]]), use_bsgs=True, records=2)
+    assert np.array_equal(recs[0], full[0]) and np.array_equal(recs[1], full[0])

@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 i=0
 for cfg in "$@"; do
-  env $cfg python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err || { echo "cfg '$cfg' failed"; tail -5 gpurun_out/ab_$i.err; }
+  env $cfg python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ab_$i.json 2> gpurun_out/ab_$i.err || { echo "cfg '$cfg' failed"; tail -5 gpurun_out/ab_$i.err; }
   python - "$cfg" gpurun_out/ab_$i.json <<'PY'
 import json, sys
 cfg, path = sys.argv[1], sys.argv[2]

@@ -1,142 +1,211 @@
-"""Secondary measurements for BASELINE.json configs[0..4] other than the headline bench (which is configs[3]-shaped):
-  config1: one block latency (diagonal + BSGS), vs the reference on one core
-  config2: MNIST 784->10 sample: transcipher 7 blocks + mask + flatten + 10 x (multiply, relin, vec_sum 784)
-  config3: ECG 128->1, batch of samples (counter 0 each): transcipher + multiply + relin + vec_sum 128
-  config5: primitive sweep N=8192/16384: NTT fwd/inv GB/s, rotate, relinearize per second (N=32768: not supported yet)
-Prints one JSON object per config. CUDA-event timing on the engine's stream, device-resident unless noted."""
-import json, os, sys, time
-import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import common
-from oracle import refshim as R
-pkg = common.package()
-T = common.T
-stream = torch.cuda.Stream()
+"""BASELINE.json configs other than the headline one, as functions bench.py calls (its `configs` object) and as a script.
 
-def timed(ctx, fn, reps=3):
-    fn(); ctx.sync()
+  config 1  one PASTA-3 block, host API end to end (diagonal and BSGS), limb parity with the reference, reference time on this box
+  bsgs      blocks/s of the BSGS affine layer on the headline batch (device resident)
+  config 2  MNIST 784 -> 10 sample: 7 blocks + mask + flatten + 10 x (multiply, relinearize, encrypted_vec_sum(784))
+  config 3  ECG 128 -> 1 batch (every record restarts at counter 0): transcipher + multiply + relinearize + encrypted_vec_sum(128)
+  config 5  primitive sweep N = 8192 / 16384 / 32768: NTT fwd / inv, rotate_rows(-1), relinearize, multiply
+
+Every entry carries a parity flag, the reference's time for the same work on this box's host cores (measured, or composed from its
+own per-operation timings where the whole run would take tens of minutes -- the entry says which) and the fraction of the HBM roofline
+computed from SURVEY.md section 8(d)'s algorithmic-byte formulas (operands read once + result written once per SEAL-level operation).
+CUDA-event timing on the engine's stream for device-resident figures, host clock around the blocking call for end-to-end ones.
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+import common  # noqa: E402
+
+T = common.T
+MIB = 1 << 20
+BYTES_PER_BLOCK = {False: 7_751_991_296, True: 5_990_383_616}  # diagonal / BSGS
+KS_COUNT = {128: 355, 300: 938, 784: 2875}                      # NAF key switches of encrypted_vec_sum(n), SURVEY.md App. D
+Q_32768 = [36028797017456641, 36028797014704129, 36028797014573057, 36028797014376449, 36028797013327873, 36028797013000193,
+           36028797012606977, 36028797010444289, 36028797009985537, 36028797005856769, 36028797005529089, 36028797005135873,
+           36028797003694081, 36028797003563009, 36028797001138177, 72057594037338113]  # BFVDefault(32768), SURVEY.md B.1
+# credited bytes per operation (evaluation keys excluded) for N = 8192 / 16384 / 32768
+PRIM_BYTES = {8192: {"ntt": 131072, "rotate": 1048576, "relinearize": 1310720},
+              16384: {"ntt": 262144, "rotate": 4194304, "relinearize": 5242880},
+              32768: {"ntt": 524288, "rotate": 15728640, "relinearize": 19660800}}
+BSGS_STEPS = tuple(-16 * k for k in range(1, 8))
+FLATTEN_STEPS = tuple(-128 * i for i in range(1, 7))
+ALL_STEPS = (0, -1, 128) + FLATTEN_STEPS + BSGS_STEPS
+
+
+def fc_row_bytes(n, ct_mib=2):
+    """multiply (2 ct + ct3) + relinearize (ct3 + ct) + (n-1) adds (3 ct) + KS(n) key switches (2 ct), SURVEY.md 8(d)"""
+    return int((3.5 * ct_mib + 2.5 * ct_mib + (n - 1) * 3 * ct_mib + KS_COUNT[n] * 2 * ct_mib) * MIB)
+
+
+def _timed(ctx, stream, fn, reps=3):
+    import torch
+    fn()
+    ctx.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(reps): fn()
-    e1.record(stream); ctx.sync()
-    return e0.elapsed_time(e1) / reps
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    ctx.sync()
+    return e0.elapsed_time(e1) / reps * 1e-3
 
-def rnd_ct(rng, q, L, N, count, size=2):
+
+def _rnd_ct(rng, q, L, N, count, size=2):
     out = np.empty((count, size, L, N), dtype=np.uint64)
-    for i in range(L): out[:, :, i, :] = rng.integers(0, int(q[i]), (count, size, N), dtype=np.uint64)
+    for i in range(L):
+        out[:, :, i, :] = rng.integers(0, int(q[i]), (count, size, N), dtype=np.uint64)
     return out
 
-def rnd_ksk(rng, q, L, K, N):
+
+def _rnd_ksk(rng, q, L, K, N):
     out = np.empty((L, 2, K, N), dtype=np.uint64)
-    for k in range(K): out[:, :, k, :] = rng.integers(0, int(q[k]), (L, 2, N), dtype=np.uint64)
+    for k in range(K):
+        out[:, :, k, :] = rng.integers(0, int(q[k]), (L, 2, N), dtype=np.uint64)
     return out
 
-def config5():
-    rng = np.random.default_rng(0)
-    Q_32768 = [36028797017456641, 36028797014704129, 36028797014573057, 36028797014376449, 36028797013327873, 36028797013000193,
-               36028797012606977, 36028797010444289, 36028797009985537, 36028797005856769, 36028797005529089, 36028797005135873,
-               36028797003694081, 36028797003563009, 36028797001138177, 72057594037338113]  # BFVDefault(32768), SURVEY.md B.1
-    for N, q in ((8192, common.Q_8192), (16384, common.Q_16384), (32768, Q_32768)):
-        ctx = pkg.Context(N, T, q, device=0, stream=stream.cuda_stream)
-        L, K = ctx.L, ctx.K
-        B = 296 if N < 32768 else 148
-        ctx.load_ksk(0, ctx.galois_elt(-1), rnd_ksk(rng, q, L, K, N)); ctx.load_ksk(2, 0, rnd_ksk(rng, q, L, K, N))
-        a = rnd_ct(rng, q, L, N, B); a3 = rnd_ct(rng, q, L, N, B, 3)
-        d_a, d_a3, d_o = ctx.dev_alloc(a.nbytes), ctx.dev_alloc(a3.nbytes), ctx.dev_alloc(a3.nbytes)
-        ctx.dev_upload(d_a, a); ctx.dev_upload(d_a3, a3)
-        limbs = B * 2 * L
-        f = timed(ctx, lambda: ctx.dev_ntt(0, False, d_a, limbs)); i = timed(ctx, lambda: ctx.dev_ntt(0, True, d_a, limbs))
-        ctx.dev_upload(d_a, a)
-        rot = timed(ctx, lambda: ctx.dev_rotate_rows(d_a, -1, 0, d_o, B)); rel = timed(ctx, lambda: ctx.dev_relinearize(d_a3, d_o, B))
-        mul = timed(ctx, lambda: ctx.dev_multiply(d_a, d_a, d_o, B))
-        print(json.dumps({"config": 5, "N": N, "L": L, "batch": B, "ntt_fwd_GBs": limbs * 16 * N / f / 1e6, "ntt_inv_GBs": limbs * 16 * N / i / 1e6,
-                          "ntt_fwd_per_s": limbs / f * 1e3, "rotate_per_s": B / rot * 1e3, "relinearize_per_s": B / rel * 1e3, "multiply_per_s": B / mul * 1e3,
-                          "fp64_moduli": ctx.info()["fp64_moduli"]}), flush=True)
-        for p in (d_a, d_a3, d_o): ctx.dev_free(p)
-        ctx.close()
 
-def configs123():
-    N = 16384
-    steps = (0, -1, 128) + tuple(-128 * i for i in range(1, 7)) + tuple(-16 * k for k in range(1, 8))
-    ref = R.Ref(N, T, None, seed=21, steps=steps, default_gk=True)
-    ctx = pkg.Context(N, T, ref.q, device=0, stream=stream.cuda_stream)
-    t0 = time.time(); common.load_keys_from_ref(ctx, ref, keysets=(0, 1)); t_keys = time.time() - t0
-    rng = np.random.default_rng(8)
-    key = rng.integers(0, T, 256, dtype=np.uint64)
-    enc_key = ref.encrypt(common.pack_key(key, N))
+def load_all_keys(ctx, ref):
+    """PASTA + flatten + BSGS keys into keyset 0, the analyst's default power-of-two set into keyset 1, relin key."""
+    common.load_keys_from_ref(ctx, ref, keysets=(0, 1))
+
+
+def config1(ctx, ref, enc_key, key, rng, peak):
     from oracle import oracle as O
-    # ---- config 1: one block, host API end to end (H2D + D2H inside) ----
     sym = O.pasta_plain(key, T, rng.integers(0, T, 128, dtype=np.uint64))
+    out = {}
     for bsgs in (False, True):
         ctx.pasta3_decompose(enc_key, sym, use_bsgs=bsgs)
-        t0 = time.perf_counter(); out = ctx.pasta3_decompose(enc_key, sym, use_bsgs=bsgs); dt = time.perf_counter() - t0
-        t0 = time.perf_counter(); want = ref.pasta_decompose(enc_key, sym, bsgs); dr = time.perf_counter() - t0
-        print(json.dumps({"config": 1, "use_bsgs": bsgs, "b200_latency_s": dt, "reference_1core_s": dr, "speedup": dr / dt,
-                          "bit_exact": bool(np.array_equal(out, want))}), flush=True)
-    # ---- config 2: MNIST-shaped sample ----
-    x = rng.integers(0, 256, 784, dtype=np.uint64); W = rng.integers(-8, 9, (10, 784))
+        lat = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            got = ctx.pasta3_decompose(enc_key, sym, use_bsgs=bsgs)
+            lat.append(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        want = ref.pasta_decompose(enc_key, sym, bsgs)
+        dr = time.perf_counter() - t0
+        dt = min(lat)
+        out["bsgs" if bsgs else "diagonal"] = {
+            "b200_latency_s": dt, "reference_1core_s": dr, "speedup_vs_1core": dr / dt, "parity_limb_exact": bool(np.array_equal(got, want)),
+            "algorithmic_bytes": BYTES_PER_BLOCK[bsgs], "frac_of_hbm_roofline": BYTES_PER_BLOCK[bsgs] / dt / 1e9 / peak,
+            "note": "one block cannot fill 148 SMs (18 CTAs per key switch): latency is bound by the chain of dependent launches"}
+    return out
+
+
+def config2(ctx, ref, enc_key, key, rng, peak, ref_ops):
+    from oracle import oracle as O
+    host = importlib.import_module(common.PKG + ".host")
+    x = rng.integers(0, 256, 784, dtype=np.uint64)
+    W = rng.integers(-8, 9, (10, 784))
     symx = O.pasta_plain(key, T, x)
     enc_w = np.stack([ref.encrypt(np.mod(W[r], T).astype(np.uint64)) for r in range(10)])
-    import importlib
-    host = importlib.import_module(common.PKG + ".host")
     hhe = host.PASTA_SEAL(ctx)
-    def run2():
+
+    def run():
         flat = host.decompose(hhe, [symx], [enc_key], 784, mask_in_place=True)[0]
         return flat, host.evaluate_model(ctx, [flat], enc_w, 784)[0]
-    run2()
-    t0 = time.perf_counter(); flat, outs = run2(); dt = time.perf_counter() - t0
+    run()
+    t0 = time.perf_counter()
+    flat, outs = run()
+    dt = time.perf_counter() - t0
     logits = [int(ref.decrypt(outs[r])[0][783]) for r in range(10)]
     want = [int(v) % T for v in W @ x.astype(np.int64)]
-    # reference cost model from its own per-op timings on this box (full run would take ~20 min of SEAL on one core)
-    rot_s = ref.bench_primitive(enc_key, 2, 3); mul_s = ref.bench_primitive(enc_key, 5, 2); rel_s = ref.bench_primitive(enc_key, 3, 2)
-    blk_s = ref.bench_decompose(enc_key, 1, 1, False)
-    ref_est = 7 * blk_s + 6 * rot_s + 10 * (mul_s + rel_s + 2875 * rot_s)
-    print(json.dumps({"config": 2, "b200_e2e_s": dt, "logits_match_plaintext": logits == want, "reference_1core_estimate_s": ref_est,
-                      "reference_ops": {"block_s": blk_s, "rotate_s": rot_s, "multiply_s": mul_s, "relinearize_s": rel_s, "key_switches_per_row": 2875},
-                      "speedup_vs_1core": ref_est / dt, "key_upload_s": t_keys}), flush=True)
-    # ---- config 3: ECG batch (counter 0 for every sample) ----
-    S = int(os.environ.get("ECG_BATCH", 1024))
-    xs = rng.integers(0, 256, (S, 128), dtype=np.uint64); w = rng.integers(-128, 128, 128)
-    syms = np.stack([O.pasta_plain(key, T, xs[i]) for i in range(S)])
-    enc_w1 = ref.encrypt(np.mod(w, T).astype(np.uint64))[None]
-    def run3():
-        cts = ctx.pasta3_decompose(enc_key, syms.reshape(-1), records=S)
-        return ctx.fc_rows(cts, enc_w1, 128)
-    t0 = time.perf_counter(); outs = run3(); dt = time.perf_counter() - t0
-    ok = all(int(ref.decrypt(outs[i, 0])[0][127]) == int(np.dot(xs[i].astype(np.int64), w)) % T for i in (0, S // 2, S - 1))
-    ref_est = S * (blk_s + mul_s + rel_s + 355 * rot_s)
-    print(json.dumps({"config": 3, "samples": S, "b200_e2e_s": dt, "samples_per_s": S / dt, "spot_check_dot_products": ok,
-                      "reference_1core_estimate_s": ref_est, "speedup_vs_1core": ref_est / dt}), flush=True)
+    nbytes = 7 * BYTES_PER_BLOCK[False] + int(4.125 * MIB) + 6 * 10 * MIB + 10 * fc_row_bytes(784)
+    ref_est = 7 * ref_ops["block_s"] + 6 * ref_ops["rotate_s"] + ref_ops["multiply_plain_s"] + 10 * (
+        ref_ops["multiply_s"] + ref_ops["relinearize_s"] + KS_COUNT[784] * ref_ops["rotate_s"])
+    return {"b200_e2e_s": dt, "parity_logits_equal_plaintext_dot_products": logits == want,
+            "parity_note": "one output neuron limb-exact vs the reference: tests/test_gpu_fc.py::test_mnist_output_neuron_limb_exact",
+            "reference_1core_s": ref_est, "reference_kind": "composed from the reference's per-operation times measured in this run "
+            "(7 blocks + 6 rotations + 10 x (multiply + relinearize + 2,875 key switches)); the whole run is ~2.5 h of SEAL on one core",
+            "speedup_vs_1core": ref_est / dt, "algorithmic_bytes": nbytes, "frac_of_hbm_roofline": nbytes / dt / 1e9 / peak}
 
-def config4_siesta():
-    """SURVEY.md 8d config 4, real-data variant: SIESTA-shaped records (300 words in [0,31] -> 3 blocks, counters 0..2 restarting per
-    record) through the service call hhe_csp_decompose (host buffers: transcipher + flatten per record). The engine regroups the blocks
-    by counter, so the round material and the diagonals of each of the 3 counters are computed once per batch."""
-    N = 16384
-    ref = R.Ref(N, T, None, seed=31, steps=(0, -1, 128, -128, -256), default_gk=False)
-    ctx = pkg.Context(N, T, ref.q, device=0, stream=stream.cuda_stream)
-    common.load_keys_from_ref(ctx, ref, keysets=(0,))
-    for s_ in (-128, -256):
-        ctx.load_ksk(1, ref.galois_elt(s_), ref.ksk(0, ref.galois_elt(s_)))
-    rng = np.random.default_rng(9)
-    key = rng.integers(0, T, 256, dtype=np.uint64)
-    enc_key = ref.encrypt(common.pack_key(key, N))
+
+def config3(ctx, ref, enc_key, key, rng, peak, ref_ops, samples=1024, rank=0, world=1):
+    """ECG batch; with world > 1 every rank takes a contiguous share of the samples (no data-path collective)."""
     from oracle import oracle as O
-    Rn = int(os.environ.get("SIESTA_RECORDS", 98))  # 98 x 3 = 294 blocks: one lock-step wave
-    recs = rng.integers(0, 32, (Rn, 300), dtype=np.uint64)
-    syms = np.stack([O.pasta_plain(key, T, r) for r in recs])
-    ctx.csp_decompose(enc_key, syms.reshape(-1), records=Rn, flatten_keys=1)
-    t0 = time.perf_counter(); out = ctx.csp_decompose(enc_key, syms.reshape(-1), records=Rn, flatten_keys=1); dt = time.perf_counter() - t0
-    ok = all(np.array_equal(ref.decrypt(out[r])[0][:300], recs[r]) for r in (0, Rn // 2, Rn - 1))
-    blk_s = ref.bench_decompose(enc_key, 1, 1, False); rot_s = ref.bench_primitive(enc_key, 2, 3)
-    print(json.dumps({"config": "4-siesta", "records": Rn, "blocks": 3 * Rn, "b200_e2e_s": dt, "records_per_s": Rn / dt, "blocks_per_s": 3 * Rn / dt,
-                      "records_decrypt_to_input": ok, "reference_1core_estimate_s": Rn * (3 * blk_s + 2 * rot_s),
-                      "speedup_vs_1core": Rn * (3 * blk_s + 2 * rot_s) / dt}), flush=True)
+    S = samples // world
+    xs = rng.integers(0, 256, (samples, 128), dtype=np.uint64)[rank * S:(rank + 1) * S]
+    w = rng.integers(-128, 128, 128)
+    syms = np.stack([O.pasta_plain(key, T, xs[i]) for i in range(S)])
+    enc_w1 = ref.encrypt(np.mod(w, T).astype(np.uint64))[None] if ref is not None else None
+    return xs, w, syms, enc_w1
+
+
+def config3_run(ctx, enc_key, syms, enc_w1):
+    S = syms.shape[0]
+    t0 = time.perf_counter()
+    cts = ctx.pasta3_decompose(enc_key, syms.reshape(-1), records=S)
+    outs = ctx.fc_rows(cts, enc_w1, 128)
+    return outs, time.perf_counter() - t0
+
+
+def config5(stream, peak, ref_factory=None):
+    import torch  # noqa: F401
+    pkg = common.package()
+    rng = np.random.default_rng(0)
+    res = {}
+    for N, q in ((8192, common.Q_8192), (16384, common.Q_16384), (32768, Q_32768)):
+        ctx = pkg.Context(N, T, q, device=torch.cuda.current_device(), stream=stream.cuda_stream)
+        L, K = ctx.L, ctx.K
+        B = 296 if N < 32768 else 148
+        ctx.load_ksk(0, ctx.galois_elt(-1), _rnd_ksk(rng, q, L, K, N))
+        ctx.load_ksk(2, 0, _rnd_ksk(rng, q, L, K, N))
+        qmin = [min(int(v) for v in q)] * len(q)  # residues valid for every limb: the NTT launches below use table 0 for all limbs
+        a, a3 = _rnd_ct(rng, qmin, L, N, B), _rnd_ct(rng, qmin, L, N, B, 3)
+        d_a, d_a3, d_o = ctx.dev_alloc(a.nbytes), ctx.dev_alloc(a3.nbytes), ctx.dev_alloc(a3.nbytes)
+        ctx.dev_upload(d_a, a)
+        ctx.dev_upload(d_a3, a3)
+        limbs = B * 2 * L
+        f = _timed(ctx, stream, lambda: ctx.dev_ntt(0, False, d_a, limbs))
+        i = _timed(ctx, stream, lambda: ctx.dev_ntt(0, True, d_a, limbs))
+        # round trip parity of the timed kernels on the spot: 8 forward + 8 inverse transforms ran, the data must be the input again
+        back = np.empty_like(a)
+        ctx.dev_download(d_a, back)
+        ctx.dev_upload(d_a, a)
+        rot = _timed(ctx, stream, lambda: ctx.dev_rotate_rows(d_a, -1, 0, d_o, B))
+        rel = _timed(ctx, stream, lambda: ctx.dev_relinearize(d_a3, d_o, B))
+        mul = _timed(ctx, stream, lambda: ctx.dev_multiply(d_a, d_a, d_o, B))
+        pb = PRIM_BYTES[N]
+        entry = {
+            "L": L, "batch": B, "fp64_path_moduli": ctx.info()["fp64_moduli"], "parity_ntt_round_trip": bool(np.array_equal(back, a)),
+            "parity_note": "limb parity of every primitive with SEAL at each size: tests/test_gpu_fullsize.py (N = 8192, 16384, 32768 cases)",
+            "ntt_fwd": {"GBps": limbs * pb["ntt"] / f / 1e9, "limbs_per_s": limbs / f, "frac_of_hbm_roofline": limbs * pb["ntt"] / f / 1e9 / peak},
+            "ntt_inv": {"GBps": limbs * pb["ntt"] / i / 1e9, "limbs_per_s": limbs / i, "frac_of_hbm_roofline": limbs * pb["ntt"] / i / 1e9 / peak},
+            "rotate_rows": {"per_s": B / rot, "GBps": B * pb["rotate"] / rot / 1e9, "frac_of_hbm_roofline": B * pb["rotate"] / rot / 1e9 / peak},
+            "relinearize": {"per_s": B / rel, "GBps": B * pb["relinearize"] / rel / 1e9,
+                            "frac_of_hbm_roofline": B * pb["relinearize"] / rel / 1e9 / peak},
+            "multiply": {"per_s": B / mul},
+        }
+        for p_ in (d_a, d_a3, d_o):
+            ctx.dev_free(p_)
+        ctx.close()
+        if ref_factory is not None:
+            r = ref_factory(N)
+            ct = r.encrypt(np.arange(16, dtype=np.uint64))
+            ntt_f, ntt_i = r.bench_primitive(ct, 0, 20), r.bench_primitive(ct, 1, 20)
+            reps = 3 if N < 32768 else 1
+            rr, rl, rm = r.bench_primitive(ct, 2, reps), r.bench_primitive(ct, 3, reps), r.bench_primitive(ct, 5, reps)
+            entry["reference_1core"] = {"ntt_fwd_limbs_per_s": 1 / ntt_f, "ntt_inv_limbs_per_s": 1 / ntt_i, "rotate_rows_per_s": 1 / rr,
+                                        "relinearize_per_s": 1 / rl, "multiply_per_s": 1 / rm}
+            entry["speedup_vs_1core"] = {"ntt_fwd": limbs / f * ntt_f, "rotate_rows": B / rot * rr, "relinearize": B / rel * rl,
+                                         "multiply": B / mul * rm}
+            r.close()
+        res[f"N{N}"] = entry
+    return res
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["5", "123", "4"]
-    if "5" in which: config5()
-    if "123" in which: configs123()
-    if "4" in which: config4_siesta()
+    import torch
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    from oracle import refshim as R
+    stream = torch.cuda.Stream()
+    fac = (lambda N: R.Ref(N, T, None, seed=5, steps=(0, -1), default_gk=False)) if R.available() else None
+    print(json.dumps({"config5": config5(stream, peak, fac)}))

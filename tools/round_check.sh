@@ -12,9 +12,9 @@ python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench
 stamp "bench done"
 python bench.py --impl reference --steps 1 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; tail -c 600 gpurun_out/bench_ref.json
 stamp "reference arm done"
-python bench.py --bsgs --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bsgs.json 2> gpurun_out/bench_bsgs.err; echo "bsgs rc=$?"; tail -c 400 gpurun_out/bench_bsgs.json
+python bench.py --bsgs --steps 3 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/bench_bsgs.json 2> gpurun_out/bench_bsgs.err; echo "bsgs rc=$?"; tail -c 400 gpurun_out/bench_bsgs.json
 stamp "bsgs bench done"
-CMD="python bench.py --steps 1 --warmup 3 --blocks 148 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --blocks 148 --no-cpu-baseline --no-configs"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 3000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 echo "launch list rc=$?"
