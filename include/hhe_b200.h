@@ -192,6 +192,17 @@ int hhe_profile_report(hhe_ctx *ctx, char *buf, size_t cap);
 int hhe_pasta3_plain(hhe_ctx *ctx, const uint64_t *key256, const uint64_t *in, size_t n_words, uint64_t nonce, uint64_t first_counter,
                      int decrypt, uint64_t *out);
 
+/* seal::Encryptor::encrypt with a public key (BFV; libs/seal/include/SEAL-4.0/seal/encryptor.h:132, seal/util/rlwe.h:52-105) for
+ * bulk data owners and analysts: the operation behind sealhelper::encrypt_weight_mat (src/util/sealhelper.cpp:123-142) and
+ * pastahelper::encrypt_symmetric_key (src/util/pastahelper.cpp:355-377). pk = seal::PublicKey::data(): u64[2][K][N], NTT form.
+ * seeds: u64[count][8], one seal::prng_seed_type per ciphertext for SEAL's Blake2xb generator (NULL: 64 bytes per ciphertext
+ * from the operating system, as SEAL does). For the same seed the ciphertext is bit-identical to SEAL's: the Blake2xb stream, the
+ * ternary and centred-binomial samplers and their draw order are reproduced on the GPU. plain: u64[count][N] coefficients < t.
+ * hhe_encrypt_slots = BatchEncoder::encode + encrypt (slots: u64[count][n_slots], values < t). */
+int hhe_encrypt(hhe_ctx *ctx, const uint64_t *pk, const uint64_t *seeds, const uint64_t *plain, size_t count, uint64_t *out);
+int hhe_encrypt_slots(hhe_ctx *ctx, const uint64_t *pk, const uint64_t *seeds, const uint64_t *slots, size_t n_slots, size_t count,
+                      uint64_t *out);
+
 /* ---- plain PASTA-3 material (device SHAKE128 + matrix generation, for parity tests of that kernel) ---- */
 /* mat1[128*128], mat2[128*128], rc[256] as u32 for (nonce, counter, layer 0..3) */
 int hhe_pasta_layer_material(hhe_ctx *ctx, uint64_t nonce, uint64_t counter, int layer, uint32_t *mat1, uint32_t *mat2,

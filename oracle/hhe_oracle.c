@@ -446,17 +446,23 @@ void hor_add_plain(const hor_ctx *c, const uint64_t *a, const uint64_t *pt, uint
   }
 }
 
-/* centred ("fast plain") lift of a plaintext into limb i and forward NTT (Evaluator::multiply_plain_normal) */
-static void lift_ntt(const hor_ctx *c, const u64 *pt, int i, u64 *dst) {
-  for (u64 j = 0; j < c->N; j++) dst[j] = pt[j] >= c->upper_half_threshold ? pt[j] + c->upper_half_increment[i] : pt[j];
+/* centred ("fast plain") lift of a plaintext into limb i and forward NTT (Evaluator::multiply_plain_normal).
+ * mono != 0: the plaintext has exactly one nonzero coefficient. SEAL then takes its monomial branch
+ * (negacyclic_multiply_poly_mono_coeffmod) and, with fast plain lift (every q_i > t), multiplies by the coefficient AS IT IS,
+ * also when it lies in the upper half: no centred lift. The product with m X^e equals the NTT product with the un-lifted
+ * plaintext, so the same code serves; only the lift is skipped. (Verified limb-exact against the reference for t - 1.) */
+static void lift_ntt(const hor_ctx *c, const u64 *pt, int i, int mono, u64 *dst) {
+  for (u64 j = 0; j < c->N; j++) dst[j] = (!mono && pt[j] >= c->upper_half_threshold) ? pt[j] + c->upper_half_increment[i] : pt[j];
   ntt_fwd(&c->qt[i], c->N, dst);
 }
 
 /* Evaluator::multiply_plain on a coefficient-form ciphertext (evaluator.h:729) */
 void hor_multiply_plain(const hor_ctx *c, const uint64_t *a, const uint64_t *pt, uint64_t *out) {
   u64 *m = malloc(sizeof(u64) * c->N), *x = malloc(sizeof(u64) * c->N);
+  u64 nonzero = 0;
+  for (u64 j = 0; j < c->N; j++) nonzero += pt[j] != 0;
   for (int i = 0; i < c->L; i++) {
-    lift_ntt(c, pt, i, m);
+    lift_ntt(c, pt, i, nonzero == 1, m);
     for (int p = 0; p < 2; p++) {
       memcpy(x, LIMB(a, p, i), sizeof(u64) * c->N);
       ntt_fwd(&c->qt[i], c->N, x);

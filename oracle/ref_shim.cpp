@@ -229,6 +229,11 @@ int ref_list_galois(void *h, int kind, uint32_t *elts) {
   return n;
 }
 
+void ref_public_key(void *h, uint64_t *out) {  // [2][K][N], NTT form, key level (seal::PublicKey::data())
+  Ref *r = static_cast<Ref *>(h);
+  std::memcpy(out, r->pk.data().data(), sizeof(uint64_t) * 2 * r->K * r->N);
+}
+
 void ref_secret_key(void *h, uint64_t *out) {  // [K][N], NTT form (SEAL's storage)
   Ref *r = static_cast<Ref *>(h);
   std::memcpy(out, r->sk.data().data(), sizeof(uint64_t) * r->K * r->N);

@@ -58,6 +58,7 @@ class Ref:
         if not self.h:
             raise RefError(l.ref_last_error().decode())
         self.h = C.c_void_p(self.h)
+        self.seed = int(seed)
         info = np.zeros(4, dtype=np.uint64)
         l.ref_info(self.h, _p(info))
         self.N, self.L, self.K, self.t = (int(x) for x in info)
@@ -100,6 +101,16 @@ class Ref:
         arr = (C.c_uint32 * max(1, n))()
         lib().ref_list_galois(self.h, kind, arr)
         return [int(arr[i]) for i in range(n)]
+
+    def public_key(self):
+        out = np.zeros((2, self.K, self.N), dtype=np.uint64)
+        lib().ref_public_key(self.h, _p(out))
+        return out
+
+    def prng_seed(self):
+        """The prng_seed_type ref_create gives its Blake2xbPRNGFactory: every generator SEAL creates from it (one per encryption)
+        starts from this seed."""
+        return np.array([(self.seed * 0x9E3779B97F4A7C15 + i) % (1 << 64) for i in range(8)], dtype=np.uint64)
 
     def secret_key(self):
         out = np.zeros((self.K, self.N), dtype=np.uint64)

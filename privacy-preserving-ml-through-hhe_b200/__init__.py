@@ -32,7 +32,7 @@ SYMBOLS = [
     "hhe_dev_relinearize", "hhe_dev_multiply", "hhe_dev_pasta3_decompose", "hhe_launch_count",
     "hhe_pasta_layer_material", "hhe_profile_enable", "hhe_profile_reset", "hhe_profile_report", "hhe_clear_keyset",
     "hhe_seal_parms_id", "hhe_seal_ct_save_bound", "hhe_seal_ct_save", "hhe_seal_ct_load", "hhe_seal_keys_unpack",
-    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized", "hhe_pasta3_plain", "hhe_build_is_cuda",
+    "hhe_load_seal_keys", "hhe_pasta3_decompose_serialized", "hhe_pasta3_plain", "hhe_build_is_cuda", "hhe_encrypt", "hhe_encrypt_slots",
 ]
 
 
@@ -184,6 +184,31 @@ class Context:
         o = np.zeros(w.size, dtype=np.uint64)
         self._chk(self.lib.hhe_pasta3_plain(self.h, pk, pw, C.c_size_t(w.size), C.c_uint64(nonce), C.c_uint64(first_counter),
                                             int(decrypt), o.ctypes.data_as(_u64p)))
+        return o
+
+    def encrypt(self, pk, plain=None, slots=None, seeds=None):
+        """seal::Encryptor::encrypt with the public key `pk` ([2][K][N], NTT form) on the GPU. Either `plain` ([count][N] plaintext
+        coefficients) or `slots` ([count][n] batch slots, encoded first). `seeds` ([count][8] uint64): one SEAL prng_seed_type per
+        ciphertext (None: from the operating system). Bit-identical to SEAL for the same seed."""
+        k, pk_p = _arr(pk)
+        if k.size != 2 * self.K * self.N:
+            raise HheInvalidArgument(HHE_ERR_INVALID, "public key has the wrong size")
+        src = np.ascontiguousarray(plain if slots is None else slots, dtype=np.uint64)
+        src = src[None] if src.ndim == 1 else src
+        count = src.shape[0]
+        sp = None
+        if seeds is not None:
+            sd = np.ascontiguousarray(seeds, dtype=np.uint64).reshape(count, 8)
+            sp = sd.ctypes.data_as(_u64p)
+        o = np.zeros((count, 2, self.L, self.N), dtype=np.uint64)
+        if slots is None:
+            if src.shape[1] != self.N:
+                raise HheInvalidArgument(HHE_ERR_INVALID, "plaintext must have N coefficients")
+            rc = self.lib.hhe_encrypt(self.h, pk_p, sp, src.ctypes.data_as(_u64p), C.c_size_t(count), o.ctypes.data_as(_u64p))
+        else:
+            rc = self.lib.hhe_encrypt_slots(self.h, pk_p, sp, src.ctypes.data_as(_u64p), C.c_size_t(src.shape[1]), C.c_size_t(count),
+                                            o.ctypes.data_as(_u64p))
+        self._chk(rc)
         return o
 
     def clear_keyset(self, kind):

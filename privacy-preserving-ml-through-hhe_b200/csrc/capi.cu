@@ -1,5 +1,6 @@
 // C ABI of libhhe_b200.so (include/hhe_b200.h): host-buffer marshalling around hhe::Engine.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -307,13 +308,25 @@ int hhe_multiply_plain(hhe_ctx *ctx, const uint64_t *a, const uint64_t *pt, uint
     Engine &e = E(ctx);
     Engine::Scope sc(e);
     const size_t w = count * e.ct_words(), N = e.params().N;
+    // SEAL's multiply_plain: a zero plaintext is refused; a MONOMIAL plaintext (one nonzero coefficient) takes the
+    // negacyclic_multiply_poly_mono_coeffmod branch, which with fast plain lift multiplies by the coefficient as it is
+    // (no centred lift even in the upper half): flagged per item for the lift kernel
+    std::vector<u32> mono(count, 0);
+    bool any_mono = false;
     for (size_t it = 0; it < count; ++it) {
-      bool zero = true;
-      for (size_t j = 0; j < N && zero; ++j) zero = pt[it * N + j] == 0;
-      if (zero) throw std::logic_error("result ciphertext is transparent");
+      size_t nz = 0;
+      for (size_t j = 0; j < N; ++j) nz += pt[it * N + j] != 0;
+      if (!nz) throw std::logic_error("result ciphertext is transparent");
+      mono[it] = nz == 1;
+      any_mono = any_mono || nz == 1;
     }
     u64 *da = up(e, a, w), *dp = up(e, pt, count * N), *dout = e.scratch(w);
-    e.multiply_plain(da, dp, N, dout, count);
+    u32 *dm = nullptr;
+    if (any_mono) {
+      dm = reinterpret_cast<u32 *>(e.scratch((count + 1) / 2));
+      e.dev().h2d(dm, mono.data(), count * 4);
+    }
+    e.multiply_plain(da, dp, N, dout, count, dm);
     down(e, out, dout, w);
     e.dev().sync();
   });
@@ -655,6 +668,73 @@ int hhe_pasta_layer_material(hhe_ctx *ctx, uint64_t nonce, uint64_t counter, int
     e.dev().d2h(rc, d_mat + kMatWords + layer * 2 * kPastaT, 2 * kPastaT * 4);
     e.dev().sync();
   });
+}
+
+// ---------------------------------------------------------------------------------------------- client side: encryption
+namespace {
+// seeds for callers that pass none: 64 bytes per ciphertext from the operating system, as SEAL's random_uint64() (getrandom /
+// /dev/urandom) seeds a fresh Blake2xbPRNG for every encryption
+void os_random(u64 *out, size_t words) {
+  FILE *f = std::fopen("/dev/urandom", "rb");
+  if (!f || std::fread(out, 8, words, f) != words) {
+    if (f) std::fclose(f);
+    throw std::runtime_error("cannot read /dev/urandom for the encryption seeds");
+  }
+  std::fclose(f);
+}
+
+void encrypt_host(Engine &e, const uint64_t *pk, const uint64_t *seeds, const uint64_t *plain, const uint64_t *slots, size_t n_slots,
+                  size_t count, uint64_t *out) {
+  const Params &p = e.params();
+  if (!pk || !out || (!plain && !slots)) throw std::invalid_argument("null buffer");
+  if (!count) return;
+  const size_t N = p.N, ctw = e.ct_words();
+  if (slots) {
+    if (n_slots > N) throw std::invalid_argument("values_matrix size exceeds slot count");
+    for (size_t i = 0; i < n_slots * count; ++i)
+      if (slots[i] >= p.t) throw std::invalid_argument("input value is larger than plain_modulus");
+  } else {
+    for (size_t i = 0; i < N * count; ++i)
+      if (plain[i] >= p.t) throw std::invalid_argument("plain is not valid for encryption parameters");
+  }
+  for (size_t i = 0; i < static_cast<size_t>(2) * p.K * N; ++i)
+    if (pk[i] >= p.q[(i / N) % p.K]) throw std::invalid_argument("public key is not valid for encryption parameters");
+  std::vector<u64> own;
+  if (!seeds) {
+    own.resize(count * 8);
+    os_random(own.data(), own.size());
+    seeds = own.data();
+  }
+  Engine::Scope sc(e);
+  u64 *d_pk = up(e, pk, static_cast<size_t>(2) * p.K * N);
+  const size_t step = static_cast<size_t>(std::max(1, e.batch_limit()));
+  OverlappedOut oo(e, std::min(step, count) * ctw, count > step);
+  size_t chunk = 0;
+  chunked(e, count, [&](size_t off, size_t nb) {
+    Engine::Scope inner(e);
+    u64 *d_seeds = up(e, seeds + off * 8, nb * 8);
+    u64 *d_pt;
+    if (slots) {
+      u64 *ds = up(e, slots + off * n_slots, std::max<size_t>(1, n_slots * nb));
+      d_pt = e.scratch(nb * N);
+      e.encode_slots(ds, n_slots, nullptr, static_cast<u32>(n_slots), d_pt, nb);
+    } else {
+      d_pt = up(e, plain + off * N, nb * N);
+    }
+    e.encrypt(d_pk, d_seeds, d_pt, nb, oo.buf(chunk));
+    oo.send(chunk++, out + off * ctw, nb * ctw);
+  });
+  oo.finish();
+}
+}  // namespace
+
+int hhe_encrypt(hhe_ctx *ctx, const uint64_t *pk, const uint64_t *seeds, const uint64_t *plain, size_t count, uint64_t *out) {
+  return guarded([&] { encrypt_host(E(ctx), pk, seeds, plain, nullptr, 0, count, out); });
+}
+
+int hhe_encrypt_slots(hhe_ctx *ctx, const uint64_t *pk, const uint64_t *seeds, const uint64_t *slots, size_t n_slots, size_t count,
+                      uint64_t *out) {
+  return guarded([&] { encrypt_host(E(ctx), pk, seeds, nullptr, slots, n_slots, count, out); });
 }
 
 // ---------------------------------------------------------------------------------------------- SEAL wire format

@@ -54,11 +54,12 @@ class Engine {
   void broadcast(const u64 *src, u64 *out, size_t words, size_t items);
   void encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items);
   void encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items);
-  void lift_ntt(const u64 *pt, u64 *D, size_t items);
+  // nolift (device, per plaintext, optional): 1 = monomial plaintext, multiplied without the centred lift as SEAL does
+  void lift_ntt(const u64 *pt, u64 *D, size_t items, const u32 *nolift = nullptr);
   void ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps = 2, size_t sum_off = 0,
                u64 *ntt_out = nullptr, const u32 *didx = nullptr);
   void ct_intt(u64 *ct, size_t items, int size = 2);
-  void multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items);
+  void multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, const u32 *nolift = nullptr);
   void galois(const u64 *a, u32 elt, u64 *out, size_t items);
   // out[c] = ModDown(sum_J NTT(target_J) * key) + base_c ; target/base given with item strides (words)
   void key_switch(const u64 *target, size_t tstride, const W2 *key, const u64 *base0, const u64 *base1, size_t bstride,
@@ -80,6 +81,8 @@ class Engine {
   void flatten(const u64 *in, size_t per, int keyset, u64 *out, size_t items);
   void vec_sum(const u64 *a, size_t n, int keyset, u64 *out, size_t items);
   void strided_copy(const u64 *src, size_t sstride, u64 *dst, size_t dstride, size_t words, size_t rows);
+  // seal::Encryptor::encrypt (public key, BFV) with SEAL's Blake2xb generator seeded per ciphertext (engine_enc.cu)
+  void encrypt(const u64 *d_pk, const u64 *d_seeds, const u64 *d_pt, size_t count, u64 *d_out);
 
   const DevConsts *dconsts() const { return dC_; }
   TwRef twref() const { return TwRef{dTw_, P_.N, f64_gmin_}; }

@@ -101,17 +101,17 @@ void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode
   });
 }
 
-void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items) {
+void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items, const u32 *nolift) {
   require_whole_limb("multiply_plain");
   if (half_fwd_) {
     HHE_DISPATCH_LOG(P_.logn - 1, {
-      LiftNttHalfBody<LOGV> body{pt, D, dC_, twref()};
+      LiftNttHalfBody<LOGV> body{pt, D, dC_, twref(), nolift};
       dev_.launch(body, items * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
     });
     return;
   }
   HHE_DISPATCH_LOG(P_.logn, {
-    LiftNttBody<LOGV> body{pt, D, dC_, twref()};
+    LiftNttBody<LOGV> body{pt, D, dC_, twref(), nolift};
     dev_.launch(body, items * P_.L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
 }
@@ -165,11 +165,11 @@ void Engine::ct_intt(u64 *ct, size_t items, int size) {
   ntt(ct, ct, items, size * P_.L, map_mod(size * P_.L, P_.L, 0), true);
 }
 
-void Engine::multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items) {
+void Engine::multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, const u32 *nolift) {
   Scope sc(*this);
   const size_t ditems = pstride ? items : 1;
   u64 *D = scratch(ditems * P_.L * P_.N);
-  lift_ntt(pt, D, ditems);
+  lift_ntt(pt, D, ditems, nolift);
   ntt_mac(a, D, pstride ? static_cast<size_t>(P_.L) * P_.N : 0, out, items, true);
   ct_intt(out, items);
 }

@@ -79,6 +79,9 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     GaloisBody gb{c1c, g1, dC_, e1_inv, nb * dw};
     dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
   }
+  // half-limb FP64 kernels: both components of the rotated ciphertext stay NTT-resident (Corr0MacHalfBody, comps = 2), the
+  // coefficient form of c1 is never stored (only its Galois image g1, the next key switch's digits)
+  const bool pair = half_fwd_ && cluster_inv_ && !getenv_flag("HHE_NO_CORR_PAIR");
   for (int i = 1; i < kPastaT; ++i) {
     launch_ks_digits(g1, dw, k1, acc, nb, c1n, dw, perm);
     // inverse NTT of the two special limbs acc[0][K-1], acc[1][K-1] (K*N words apart inside an item), then of acc[1][i<L]
@@ -88,7 +91,7 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     if (cluster_inv_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
         using Body = InvClusterBody<LOGV, PlanModDownGalois>;
-        Body body{PlanModDownGalois{acc, c1c, g1, e1, P_.logn}, dC_, twref(), pf_limbs_, static_cast<int>(nb * L)};
+        Body body{PlanModDownGalois{acc, pair ? nullptr : c1c, g1, e1, P_.logn}, dC_, twref(), pf_limbs_, static_cast<int>(nb * L)};
         dev_.launch_cluster2(body, nb * L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     } else {
@@ -101,8 +104,8 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     lift_ntt(pt, D, nd);
     if (half_fwd_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
-        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L)};
-        dev_.launch(body, nb * L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), pair ? 2 : 1, c1n};
+        dev_.launch(body, nb * L * (pair ? 4 : 2), half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     } else {
       HHE_DISPATCH_LOG(P_.logn, {
@@ -111,7 +114,7 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
       });
     }
     std::swap(c0_in, c0_out);
-    ntt_mac(c1c, D, ds, sum, nb, false, 1, dw, c1n, didx);
+    if (!pair) ntt_mac(c1c, D, ds, sum, nb, false, 1, dw, c1n, didx);
   }
   ntt(sum, state, nb, 2 * L, map_mod(2 * L, L, 0), true);
 }

@@ -5,6 +5,7 @@
 // FOR_THREADS becomes a sequential loop over the CTA's threads so the index arithmetic of every kernel can be unit
 // tested on a machine without a GPU. The emulation build is a test harness for host logic, not a CPU fallback.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDACC__) && !defined(HHE_EMULATE)
@@ -37,7 +38,7 @@ using u64 = uint64_t;
 // One thread of the CTA asks the L2 to fetch `bytes` (multiple of 16) at the 16-byte aligned global address p
 // (cp.async.bulk.prefetch.L2, SASS UBLKPF.L2): no register, no LSU slot, nothing to wait for. Kernels whose load phase is
 // a chain of dependent DRAM round trips use it to pull the operands of the CTA that will run two waves later into the L2.
-HD void cta_prefetch_l2(const void *p, size_t bytes) {
+HD void cta_prefetch_l2(const void *p, std::size_t bytes) {
 #if defined(__CUDA_ARCH__)
   if (threadIdx.x == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(static_cast<unsigned>(bytes)) : "memory");
 #else

@@ -50,7 +50,7 @@ struct LoadCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[spec
   DevMod mi, msp;
   HD double load(int j) const {
     const u64 r = csub(sp[j] + half_sp, msp.q);
-    const u64 ri = msp.q > q ? barrett64(r, mi) : r;
+    const u64 ri = msp.q > q ? (msp.q < 2 * q ? csub(r, q) : barrett64(r, mi)) : r;
     return u_to_f(sub_mod(ri, half_i, q));
   }
   HD void store(int, double) const {}
@@ -104,7 +104,9 @@ struct RawCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[speci
   HD u64 raw(int j) const { return sp[j]; }
   HD double cvt(u64 v) const {
     const u64 r = csub(v + half_sp, msp.q);
-    const u64 ri = msp.q > q ? barrett64(r, mi) : r;
+    // r < q_sp: no reduction when q_sp <= q_i, one conditional subtraction when q_sp < 2 q_i (every BFVDefault set: the primes of a
+    // set differ by at most one bit), the 128-bit Barrett reduction (integer multiplies, which stall the FP64 pipe) only otherwise
+    const u64 ri = msp.q > q ? (msp.q < 2 * q ? csub(r, q) : barrett64(r, mi)) : r;
     return u_to_f(sub_mod(ri, half_i, q));
   }
 };
@@ -1062,12 +1064,13 @@ struct LiftNttBody {
   u64 *out;       // [items][L][N]
   const DevConsts *C;
   TwRef tw;
+  const u32 *nolift;  // optional, per item: 1 = monomial plaintext, SEAL multiplies by the coefficient without the centred lift
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     u64 *sm = reinterpret_cast<u64 *>(smem);
     const int L = C->L, i = bid % L;
     const size_t item = bid / L;
-    const u64 q = C->mod[i].q, inc = q - C->t, thr = C->half_t;
+    const u64 q = C->mod[i].q, inc = q - C->t, thr = (nolift && nolift[item]) ? ~static_cast<u64>(0) : C->half_t;
     const u64 *src = pt + item * S;
     if (C->f64[i]) {
       double *fm = reinterpret_cast<double *>(smem);
@@ -1443,6 +1446,7 @@ struct LiftNttHalfBody {
   u64 *out;       // [items][L][N]
   const DevConsts *C;
   TwRef tw;
+  const u32 *nolift;  // optional, per item: 1 = monomial plaintext (no centred lift, see LiftNttBody)
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
@@ -1453,7 +1457,8 @@ struct LiftNttHalfBody {
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[i], qi = C->qinvf[i];
     const F64Tw twk = tw.fwd_f(i);
-    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawLift{pt + item * (2 * S), C->half_t, q - C->t});
+    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt,
+                            RawLift{pt + item * (2 * S), (nolift && nolift[item]) ? ~static_cast<u64>(0) : C->half_t, q - C->t});
     fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
     u64 *dst = out + static_cast<size_t>(lb) * (2 * S) + static_cast<size_t>(h) * S;
     FOR_THREADS(tid, nt) {
@@ -1527,28 +1532,39 @@ struct NttMacHalfBody {
   }
 };
 
+// Both components of the rotated ciphertext, NTT-resident, in one launch (CTA = (item, limb i, component c, half h)):
+//   c = 0:  c0n'[i] = perm(c0n[i]) + (acc0[i] - NTT_i(corr_i(r_0))) * q_sp^-1,   sum0[i] += c0n'[i] (.) D[i]
+//   c = 1:  c1n'[i] =                (acc1[i] - NTT_i(corr_i(r_1))) * q_sp^-1,   sum1[i] += c1n'[i] (.) D[i]
+// with corr_i(r)[j] = (r[j] mod q_i) - (half mod q_i), r_c = INTT(acc_c[special]) + half mod q_sp. The second line is the same
+// identity as the first: NTT_i is linear, so NTT_i of the ModDown output (INTT_i(acc1[i]) - corr_i) * q_sp^-1 needs only the
+// transform of the correction. It replaces the forward transform of the coefficient-form c1 (ntt_mac on c1c), so the chain
+// never stores or re-reads c1 in coefficient form (only its Galois image, the next key switch's digits), and the two
+// CTAs that need the diagonal's limb D[i] run next to each other (the second read is an L2 hit).
+// comps = 1 runs component 0 only (the round-1 corr0_mac).
 template <int LOGH>
 struct Corr0MacHalfBody {
-  static constexpr const char *kName = "corr0_mac";
+  static constexpr const char *kName = "corr_mac";
   static constexpr int kMaxThreads = 512, kMinBlocks = 2;
-  const u64 *acc;     // [items][2][K][N]: [0][K-1] coefficient form (after the inverse NTT), [0][i<L] NTT form
+  const u64 *acc;     // [items][2][K][N]: [c][K-1] coefficient form (after the inverse NTT), [c][i<L] NTT form
   const u64 *c0_in;   // [items][L][N] NTT form
   u64 *c0_out;        // [items][L][N]
   const u32 *perm;    // NTT-slot permutation of the Galois element
   const u64 *D;       // [items][L][N], or shared by all items (dstride = 0)
-  u64 *sum;           // [items][2][L][N], component 0 updated
+  u64 *sum;           // [items][2][L][N]
   const DevConsts *C;
   TwRef tw;
   size_t dstride;     // L*N or 0
   const u32 *didx;    // optional: item -> diagonal index
   int pf, nl;         // L2 prefetch distance in limbs (0: off), total limbs of the launch
+  int comps;          // 1: component 0 only; 2: both
+  u64 *c1_out;        // [items][L][N] NTT form of the new component 1 (comps == 2)
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
-    const int h = bid & 1, lb = bid >> 1;
+    const int h = bid & 1, c = comps == 2 ? (bid >> 1) & 1 : 0, lb = comps == 2 ? bid >> 2 : bid >> 1;
     const int L = C->L, K = C->K, i = lb % L;
     const size_t item = lb / L, N = 2 * S, hoff = static_cast<size_t>(h) * S;
-    if (pf && !h && lb + pf < nl) {  // operands of the CTA pair that runs two waves later
+    if (pf && !h && !c && lb + pf < nl) {  // operands of the CTAs that run two waves later
       const int lf = lb + pf, fi = lf % L;
       const size_t itf = lf / L;
       if (fi == 0) cta_prefetch_l2(acc + ((itf * 2) * K + (K - 1)) * N, sizeof(u64) * N);
@@ -1558,15 +1574,15 @@ struct Corr0MacHalfBody {
       cta_prefetch_l2(sum + (itf * 2 * L + fi) * N, sizeof(u64) * N);
     }
     const DevMod mi = C->mod[i], msp = C->mod[K - 1];
-    const u64 *sp = acc + ((item * 2) * K + (K - 1)) * N;
+    const u64 *sp = acc + ((item * 2 + c) * K + (K - 1)) * N;
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[i], qi = C->qinvf[i];
     const F64Tw twk = tw.fwd_f(i);
-    const u64 *a0 = acc + ((item * 2) * K + i) * N + hoff;
+    const u64 *a0 = acc + ((item * 2 + c) * K + i) * N + hoff;
     const u64 *cin = c0_in + (item * L + i) * N;
-    u64 *cout = c0_out + (item * L + i) * N + hoff;
+    u64 *cout = (c ? c1_out : c0_out) + (item * L + i) * N + hoff;
     const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + hoff;
-    u64 *s0 = sum + (item * 2 * L + i) * N + hoff;
+    u64 *s0 = sum + ((item * 2 + c) * L + i) * N + hoff;
     fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
     fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
     const u32 *pm = perm + hoff;
@@ -1576,12 +1592,14 @@ struct Corr0MacHalfBody {
       for (int j0 = tid; j0 < S; j0 += nt * U) {
         u32 pj[U];
         u64 cv[U], av[U], dv[U], sv[U];
+        if (!c) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) pj[u] = pm[j0 + u * nt < S ? j0 + u * nt : j0];
+          for (int u = 0; u < U; ++u) pj[u] = pm[j0 + u * nt < S ? j0 + u * nt : j0];
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * nt < S ? j0 + u * nt : j0;
-          cv[u] = cin[pj[u]];
+          cv[u] = c ? 0 : cin[pj[u]];
           av[u] = a0[j];
           dv[u] = d[j];
           sv[u] = s0[j];
@@ -1590,11 +1608,11 @@ struct Corr0MacHalfBody {
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * nt;
           if (j < S) {
-            // k0 = (acc0 - NTT(corr)) * q_sp^-1: |acc0 - NTT(corr)| <= 11q, |k0| <= 2.6q
+            // k = (acc - NTT(corr)) * q_sp^-1: |acc - NTT(corr)| <= 11q, |k| <= 2.6q
             const double k0 = f_mulmod_const(f_add(u_to_f(av[u]), -fm[pidx(j)]), isp, qd);
-            const u64 c = f_canonical(f_add(u_to_f(cv[u]), k0), qd, qi);
-            cout[j] = c;
-            s0[j] = f_canonical(f_add(f_mulmod_var(u_to_f(c), u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
+            const u64 cc = f_canonical(f_add(u_to_f(cv[u]), k0), qd, qi);
+            cout[j] = cc;
+            s0[j] = f_canonical(f_add(f_mulmod_var(u_to_f(cc), u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
           }
         }
       }
@@ -1629,7 +1647,7 @@ struct StoreModDownGalois {
     if (t >= qsp) t = f_add(t, -qsp);
     const double y = f_add(f_add(x, -t), half_i);  // |y| <= 1.4q + q_sp + q/2 < 5q
     const u64 c = f_canonical(f_mulmod_const(y, isp, q), q, qinv);
-    c1[j] = c;
+    if (c1) c1[j] = c;  // the coefficient form itself is only kept where a caller needs it
     const u32 raw = static_cast<u32>(j) * elt;
     g1[raw & nmask] = ((raw >> logn) & 1) && c ? qu - c : c;
   }
@@ -1864,7 +1882,7 @@ struct PlanModDownGalois {  // InttModDownBody
   HD StoreModDownGalois store(int lb, const DevConsts *C, int N) const {
     const int L = C->L, K = C->K, i = lb % L;
     const size_t item = lb / L, o = (item * L + i) * N;
-    return StoreModDownGalois{acc + ((item * 2 + 1) * K + (K - 1)) * N, c1 + o, g1 + o, C->n_inv_f[i], C->inv_sp_f[i], C->qf[i], C->qinvf[i],
+    return StoreModDownGalois{acc + ((item * 2 + 1) * K + (K - 1)) * N, c1 ? c1 + o : nullptr, g1 + o, C->n_inv_f[i], C->inv_sp_f[i], C->qf[i], C->qinvf[i],
                               C->qf[K - 1], static_cast<double>(C->half_sp), static_cast<double>(C->half_sp_mod_q[i]), C->mod[i].q, elt,
                               static_cast<u32>(N - 1), logn};
   }

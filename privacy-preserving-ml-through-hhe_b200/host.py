@@ -101,3 +101,52 @@ def evaluate_model(ctx: Context, decomposed, enc_weights, input_len, keyset=KEYS
     """CSP_hhe_pktnn_1fc::evaluateModel (CSP.cpp:288-323) generalised to several weight rows
     (hhe_pktnn_examples.cpp:957-992): out[sample][row] = vec_sum(relin(x * w_row), input_len)."""
     return ctx.fc_rows(np.stack(decomposed), enc_weights, input_len, keys=keyset)
+
+
+# ---- second layer of the 2-FC network (SURVEY.md section 8 f.3) ------------------------------------------------------------
+# The reference stops after fc1 ("TODO: CSP does the encrypted square activation ... TODO: CSP evaluates the encrypted fc2
+# layer", src/examples/hhe_pktnn_examples.cpp:993-997); the plaintext network is notebooks/mnist_hhe_plain.ipynb (fc1 -> x^2 ->
+# fc2). fc1 leaves hidden neuron j in slot n-1 of its own ciphertext (encrypted_vec_sum), so
+#   square activation  s_j = relinearize(square(h_j))                                   Evaluator::square + relinearize_inplace
+#   fc2 row k          out_k = sum_j sign(w) * multiply_plain(s_j, const(|w|)), w = W2[k][j]
+#                                                                    Evaluator::multiply_plain + negate_inplace + add_inplace
+# where const(m) is the CONSTANT plaintext polynomial m: it multiplies every slot by m and costs only log2(m) bits of noise
+# instead of the ~30 bits of a batch-encoded plaintext, which is what lets a second layer fit the budget left after fc1 (59-62
+# bits at N = 16384). Negative weights are taken as a product with |w| followed by a negation, NOT as the plaintext t - |w|: a
+# constant is a monomial, and SEAL multiplies monomials by the coefficient as it is (no centred lift), so t - |w| would cost 16
+# bits of noise (the engine reproduces that branch bit for bit, tests/test_oracle_vs_ref.py::test_multiply_plain_monomial_branch).
+# Zero weights are skipped (SEAL refuses a zero plaintext: "result ciphertext is transparent"). Row k's result sits in slot n-1.
+# Everything runs through the engine's existing entry points (hhe_square, hhe_relinearize, hhe_multiply_plain, hhe_negate, hhe_add).
+def square_activation(ctx: Context, hidden):
+    """relinearize(square(h)) for a batch of hidden-neuron ciphertexts [H][2][L][N]"""
+    return ctx.relinearize(ctx.square(np.asarray(hidden, dtype=np.uint64)))
+
+
+def fc2_plain_rows(ctx: Context, squared, W2):
+    """out[k] = sum_j W2[k][j] * squared[j] with small integer weights (any sign); all nonzero products of a row in one
+    batched multiply_plain, then summed."""
+    squared = np.asarray(squared, dtype=np.uint64)
+    W2 = np.asarray(W2, dtype=np.int64)
+    if W2.ndim != 2 or W2.shape[1] != squared.shape[0]:
+        raise HheInvalidArgument(-1, "fc2 weights must be [rows][hidden]")
+    out = []
+    for k in range(W2.shape[0]):
+        js = [j for j in range(W2.shape[1]) if abs(int(W2[k, j])) % ctx.t]
+        if not js:
+            raise HheInvalidArgument(-1, "fc2 row has no nonzero weight: the result would be a transparent ciphertext")
+        pts = np.zeros((len(js), ctx.N), dtype=np.uint64)
+        pts[:, 0] = [abs(int(W2[k, j])) % ctx.t for j in js]
+        terms = ctx.multiply_plain(squared[js], pts)
+        acc = None
+        for j, term in zip(js, terms):
+            if W2[k, j] < 0:
+                term = ctx.negate(term)
+            acc = term if acc is None else ctx.add(acc, term)
+        out.append(acc)
+    return np.stack(out)
+
+
+def evaluate_model_2fc(ctx: Context, decomposed, enc_w1, input_len, W2, keyset=KEYSET_1):
+    """fc1 (evaluate_model) -> square activation -> fc2 for a list of decomposed records: out[sample][row2]."""
+    h = evaluate_model(ctx, decomposed, enc_w1, input_len, keyset)  # [samples][H]
+    return np.stack([fc2_plain_rows(ctx, square_activation(ctx, h[s]), W2) for s in range(h.shape[0])])

@@ -114,6 +114,15 @@ def test_elementwise(eng, world):
     assert np.array_equal(both[0], o.add(cts[0], cts[1])) and np.array_equal(both[1], o.add(cts[1], cts[2]))
     with pytest.raises(pkg.HheLogicError):
         eng.multiply_plain(cts[0], np.zeros(N, dtype=np.uint64))
+    # SEAL's monomial branch (one nonzero coefficient: multiplied as it is, no centred lift; oracle pinned against the reference in
+    # test_oracle_vs_ref.py), mixed with a general plaintext in one batched call
+    pts = np.zeros((3, N), dtype=np.uint64)
+    pts[0, 0] = common.T - 1
+    pts[1, 9] = 5
+    pts[2] = pt
+    got = eng.multiply_plain(cts, pts)
+    for i in range(3):
+        assert np.array_equal(got[i], o.multiply_plain(cts[i], pts[i])), i
 
 
 def test_rotations(eng, world):

@@ -121,3 +121,41 @@ def test_siesta_record_flattened_limb_exact(world):
     assert np.array_equal(ctx.csp_decompose(world["enc_key"], sym, records=1, apply_mask=False, flatten_keys=0)[0], want_service)
     slots, _ = ref.decrypt(want_demo)
     assert np.array_equal(slots[:300], rec) and not slots[300:8192].any()
+
+
+def test_two_fc_layers_limb_exact_and_decrypt(world):
+    """SURVEY.md 8 f.3 at full size: transciphered input -> fc1 (4 hidden neurons, n = 128) -> encrypted square activation ->
+    fc2 (2 outputs), every ciphertext of the second layer limb-exact against SEAL running the same op sequence (square,
+    relinearize, multiply_plain by a constant plaintext, negate, add), the decrypted outputs equal to the plaintext network
+    (notebooks/mnist_hhe_plain.ipynb: fc1 -> x^2 -> fc2) and noise budget left. Weights are small so that every value fits t."""
+    ref, ctx, hhe, rng = world["ref"], world["ctx"], world["hhe"], world["rng"]
+    n, H = 128, 4
+    x = rng.integers(0, 3, n, dtype=np.uint64)
+    W1 = rng.integers(-1, 2, (H, n))
+    W2 = np.array([[1, -1, 2, 1], [-2, 1, 0, 3]])
+    h_plain = W1 @ x.astype(np.int64)
+    out_plain = W2 @ (h_plain ** 2)
+    assert np.abs(h_plain ** 2).max() < T // 2 and np.abs(out_plain).max() < T // 2, "the synthetic network must fit the plain modulus"
+    sym = O.pasta_plain(world["key"], T, x)
+    c = hhe.decomposition(sym, [world["enc_key"]], True)[0]
+    enc_w1 = np.stack([ref.encrypt(np.mod(W1[j], T).astype(np.uint64)) for j in range(H)])
+    hidden = host.evaluate_model(ctx, [c], enc_w1, n)[0]
+    sq = host.square_activation(ctx, hidden)
+    got = host.fc2_plain_rows(ctx, sq, W2)
+    for j in range(H):
+        assert np.array_equal(sq[j], ref.relinearize(ref.square(hidden[j])))
+    for k in range(2):
+        acc = None
+        for j in range(H):
+            if W2[k, j] == 0:
+                continue
+            pt = np.zeros(N, dtype=np.uint64)
+            pt[0] = abs(int(W2[k, j]))
+            term = ref.multiply_plain(sq[j], pt)
+            if W2[k, j] < 0:
+                term = ref.negate(term)
+            acc = term if acc is None else ref.add(acc, term)
+        assert np.array_equal(got[k], acc)
+        slots, budget = ref.decrypt(got[k])
+        assert budget > 0 and signed(slots[n - 1]) == int(out_plain[k])
+    assert np.array_equal(host.evaluate_model_2fc(ctx, [c], enc_w1, n, W2)[0], got)

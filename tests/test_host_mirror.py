@@ -75,3 +75,38 @@ def test_csp_call_sequence_through_the_mirror(setup):
         assert np.array_equal(out[0, r], want)
         prod = host.packed_enc_multiply(ctx, flat[0], w[r])
         assert np.array_equal(host.encrypted_vec_sum(ctx, ctx.relinearize(prod), 8), want)
+
+
+def test_second_fc_layer_composition(setup):
+    """fc1 -> encrypted square activation -> fc2 (the reference's TODO, hhe_pktnn_examples.cpp:993-997) on the
+    emulation harness against the oracle's restatement of the same SEAL op sequence (square, relinearize, multiply_plain with a
+    constant plaintext, add)."""
+    o, keys, ctx = setup["orc"], setup["keys"], setup["ctx"]
+    for elt, k in setup["gk1"].items():
+        ctx.load_ksk(pkg.KEYSET_1, elt, k)
+    ctx.load_ksk(pkg.RELIN, 0, setup["rk"])
+    rng = np.random.default_rng(11)
+    n, H = 8, 3
+    x = rng.integers(0, 4, n, dtype=np.uint64)
+    W1 = rng.integers(-2, 3, (H, n))
+    W2 = np.array([[1, -2, 3], [0, 1, -1]])
+    cx = keys.encrypt_zero_plus(o, o.encode(x))
+    enc_w1 = np.stack([keys.encrypt_zero_plus(o, o.encode(np.mod(W1[j], common.T).astype(np.uint64))) for j in range(H)])
+    got = host.evaluate_model_2fc(ctx, [cx], enc_w1, n, W2)[0]
+    # the same sequence on the oracle
+    hidden = [o.vec_sum(o.relinearize(o.multiply(cx, enc_w1[j])), n, 1) for j in range(H)]
+    sq = [o.relinearize(o.multiply(h, h)) for h in hidden]
+    for k in range(2):
+        acc = None
+        for j in range(H):
+            if W2[k, j] == 0:
+                continue
+            pt = np.zeros(N, dtype=np.uint64)
+            pt[0] = abs(int(W2[k, j]))
+            term = o.multiply_plain(sq[j], pt)
+            if W2[k, j] < 0:
+                term = o.negate(term)
+            acc = term if acc is None else o.add(acc, term)
+        assert np.array_equal(got[k], acc)
+    with pytest.raises(pkg.HheInvalidArgument):
+        host.fc2_plain_rows(ctx, np.stack(sq), [[0, 0, 0]])

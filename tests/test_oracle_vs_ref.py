@@ -117,3 +117,23 @@ def test_decomposition(pair, bsgs):
     d0, budget = ref.decrypt(got[0])
     d1, _ = ref.decrypt(got[1])
     assert budget > 0 and np.array_equal(d0[:128], pt[:128]) and np.array_equal(d1[:22], pt[128:])
+
+
+def test_multiply_plain_monomial_branch():
+    """Evaluator::multiply_plain with a MONOMIAL plaintext (one nonzero coefficient) takes SEAL's
+    negacyclic_multiply_poly_mono_coeffmod branch: with fast plain lift the coefficient is used as it is, without the centred lift,
+    also in the upper half (t - 1 multiplies by 65536, not by -1). The constant-plaintext products of the second FC layer
+    (host.fc2_plain_rows) hit this branch for every negative weight."""
+    N = 1024
+    q = common.small_params(N, 3, 48)
+    ref = R.Ref(N, common.T, q, seed=2, steps=(0,), default_gk=False)
+    orc = O.Oracle(N, common.T, q)
+    a = ref.encrypt(np.arange(50, dtype=np.uint64))
+    for coeff, pos in ((3, 0), (common.T - 1, 0), (common.T - 2, 5), (40000, N - 1)):
+        pt = np.zeros(N, dtype=np.uint64)
+        pt[pos] = coeff
+        assert np.array_equal(orc.multiply_plain(a, pt), ref.multiply_plain(a, pt)), (coeff, pos)
+    pt = np.zeros(N, dtype=np.uint64)
+    pt[0], pt[7] = common.T - 1, 2  # two coefficients: the general branch with the centred lift
+    assert np.array_equal(orc.multiply_plain(a, pt), ref.multiply_plain(a, pt))
+    ref.close()
