@@ -40,6 +40,7 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   tmem_ks_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_TMEM");
   half_fwd_ = compact_keys_ && !split_ && !getenv_flag("HHE_NO_HALF");
   if (const char *v = std::getenv("HHE_KS_THREADS")) ks_threads_ = std::atoi(v);
+  if (const char *v = std::getenv("HHE_KS_SPLIT_MAX")) ks_split_max_ = std::atoi(v);
   cluster_inv_ = half_fwd_ && !getenv_flag("HHE_NO_CLUSTER");
   dev_.strict_cluster = getenv_flag("HHE_STRICT_CLUSTER");
   dev_.ordinal = device;

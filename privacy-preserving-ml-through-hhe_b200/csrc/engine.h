@@ -53,7 +53,8 @@ class Engine {
   void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx = nullptr);
   void broadcast(const u64 *src, u64 *out, size_t words, size_t items);
   void encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items);
-  void encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items);
+  // ndiag > 1: `ndiag` consecutive diagonals diag, diag + 1, ... in one launch, pt laid out [ndiag][items][N]
+  void encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items, int ndiag = 1);
   // nolift (device, per plaintext, optional): 1 = monomial plaintext, multiplied without the centred lift as SEAL does
   void lift_ntt(const u64 *pt, u64 *D, size_t items, const u32 *nolift = nullptr);
   void ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps = 2, size_t sum_off = 0,
@@ -112,6 +113,8 @@ class Engine {
   bool split_ = false;         // N = 32768 code path (split transforms)
   bool compact_keys_ = false;
   bool tmem_ks_ = false;  // FP64 key switch with accumulators in tensor memory (keys stored group-major)
+  size_t half_smem(int logh) const { return ntt_smem_words(1 << logh) * 8; }  // dynamic shared memory of a half-limb kernel
+  int ks_split_max_ = 4;   // up to this many items a key switch runs as eight-CTA clusters, one digit per CTA (HHE_KS_SPLIT_MAX)
   int ks_threads_ = 512;   // CTA size of the tensor-memory key-switch kernel (512 x 64 registers or 256 x 128 registers)
   bool cluster_inv_ = false;  // FP64 inverse transforms as two-CTA clusters (half-limb CTAs, last stage over distributed shared memory)
   int pf_ntt_ = 0, pf_limbs_ = 0, pf_items_ = 0;  // L2 prefetch distances (limbs: plain transforms / other half-limb kernels; items: ks_digits); 0 = off

@@ -52,6 +52,14 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
 void Engine::launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, u64 *acc, size_t items, const u64 *reuse,
                               size_t reuse_stride, const u32 *perm) {
   const int K = P_.K;
+  if (tmem_ks_ && P_.L <= kKsSplitCluster && items <= static_cast<size_t>(ks_split_max_)) {
+    // service-sized request: the digit loop spread over an eight-CTA cluster (one digit's latency instead of L)
+    HHE_DISPATCH_LOG(P_.logn - 1, {
+      KsDigitsSplitBody<LOGV> body{target, tstride, reinterpret_cast<const double *>(key), acc, dC_, twref(), reuse, reuse_stride, perm};
+      dev_.launch_cluster8(body, items * K * 2 * kKsSplitCluster, half_threads(LOGV), KsDigitsSplitBody<LOGV>::smem_bytes());
+    });
+    return;
+  }
   if (tmem_ks_) {
 #ifdef HHE_CUDA
     const bool emulate = false;

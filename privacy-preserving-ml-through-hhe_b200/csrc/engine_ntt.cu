@@ -35,7 +35,7 @@ void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap 
       HHE_DISPATCH_LOG(P_.logn - 1, {
         NttFwdClusterBody<LOGV> body{in, out, dC_, twref(), map, limbs, item_stride ? item_stride : static_cast<size_t>(limbs) << (LOGV + 1),
                                      limb_stride ? limb_stride : static_cast<size_t>(2) << LOGV, pf_ntt_, static_cast<int>(items * limbs)};
-        dev_.launch_cluster2(body, items * limbs * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+        dev_.launch_cluster2(body, items * limbs * 2, half_threads(LOGV), half_smem(LOGV));
       });
       return;
     }
@@ -88,16 +88,17 @@ void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32
   if (n > P_.N) throw std::invalid_argument("values_matrix size exceeds slot count");
   require_whole_limb("encode");
   HHE_DISPATCH_LOG(P_.logn, {
-    EncodeBody<LOGV> body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, twref(), kSlots, 0, 0};
+    EncodeBody<LOGV> body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, twref(), kSlots, 0, 0, 0};
     dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
 }
 
-void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items) {
+void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items, int ndiag) {
   require_whole_limb("PASTA transciphering");
   HHE_DISPATCH_LOG(P_.logn, {
-    EncodeBody<LOGV> body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, twref(), mode, layer, diag};
-    dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+    EncodeBody<LOGV> body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, twref(), mode, layer, diag,
+                          ndiag > 1 ? static_cast<int>(items) : 0};
+    dev_.launch(body, items * static_cast<size_t>(ndiag > 1 ? ndiag : 1), ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
   });
 }
 
@@ -106,7 +107,7 @@ void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items, const u32 *nolift) {
   if (half_fwd_) {
     HHE_DISPATCH_LOG(P_.logn - 1, {
       LiftNttHalfBody<LOGV> body{pt, D, dC_, twref(), nolift};
-      dev_.launch(body, items * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      dev_.launch(body, items * P_.L * 2, half_threads(LOGV), half_smem(LOGV));
     });
     return;
   }
@@ -123,7 +124,7 @@ void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size
     HHE_DISPATCH_LOG(P_.logn - 1, {
       NttMacHalfBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out, didx,
                                 pf_limbs_, static_cast<int>(items * comps * P_.L)};
-      dev_.launch(body, items * comps * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+      dev_.launch(body, items * comps * P_.L * 2, half_threads(LOGV), half_smem(LOGV));
     });
     return;
   }

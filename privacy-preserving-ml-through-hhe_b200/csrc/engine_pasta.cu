@@ -54,7 +54,15 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   const int L = P_.L, K = P_.K;
   const size_t ctw = ct_words(), N = P_.N, dw = static_cast<size_t>(L) * N;
   const size_t ds = dw;
-  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(nd * N), *D = scratch(nd * dw);
+  // the diagonals are encoded and lifted G at a time (one launch each instead of G): G = the largest power of two <= 128 whose lifted
+  // transforms (nd x G MiB at N = 16384) stay within about 2.5 GiB -- all 128 of a layer for a service-sized request, 8 for the
+  // full 296-block batch
+  int G = 128;
+  while (G > 1 && static_cast<size_t>(G) * nd * dw * 8 > (static_cast<size_t>(5) << 29)) G >>= 1;
+  if (const char *v = std::getenv("HHE_DIAG_GROUP")) G = std::max(1, std::min(128, std::atoi(v)));
+  while (kPastaT % G) --G;
+  u64 *tmp = scratch(nb * ctw), *sum = scratch(nb * ctw), *pt = scratch(static_cast<size_t>(G) * nd * N), *Dg = scratch(static_cast<size_t>(G) * nd * dw);
+  u64 *D = Dg;
   u64 *stn = scratch(nb * ctw), *c0a = scratch(nb * dw), *c0b = scratch(nb * dw), *c1c = scratch(nb * dw), *c1n = scratch(nb * dw),
       *g1 = scratch(nb * dw), *acc = scratch(nb * 2 * K * N);
   if (N / 2 != kPastaT) {
@@ -66,8 +74,8 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   const u32 *perm = ntt_perm(e1);
   const u32 e1_inv = inv_mod_2n(e1, 2 * N);
   // step 0: sum = NTT(state) * D_0, keeping NTT(state)
-  encode_material(mat, nullptr, kDiag, layer, 0, pt, nd);
-  lift_ntt(pt, D, nd);
+  encode_material(mat, nullptr, kDiag, layer, 0, pt, nd, G);
+  lift_ntt(pt, Dg, nd * G);
   ntt_mac(state, D, ds, sum, nb, true, 2, 0, stn, didx);
   strided_copy(stn, ctw, c0a, dw, dw, nb);
   strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
@@ -82,12 +90,30 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   // half-limb FP64 kernels: both components of the rotated ciphertext stay NTT-resident (Corr0MacHalfBody, comps = 2), the
   // coefficient form of c1 is never stored (only its Galois image g1, the next key switch's digits)
   const bool pair = half_fwd_ && cluster_inv_ && !getenv_flag("HHE_NO_CORR_PAIR");
+  const bool fuse_tail = !getenv_flag("HHE_NO_ROT_TAIL");
   for (int i = 1; i < kPastaT; ++i) {
     launch_ks_digits(g1, dw, k1, acc, nb, c1n, dw, perm);
     // inverse NTT of the two special limbs acc[0][K-1], acc[1][K-1] (K*N words apart inside an item), then of acc[1][i<L]
     // with the ModDown and the next rotation's Galois map fused into the store
     ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, 2, msp2, true, static_cast<size_t>(2) * K * N,
         static_cast<size_t>(K) * N);
+    if (i % G == 0) {
+      encode_material(mat, nullptr, kDiag, layer, i, pt, nd, G);
+      lift_ntt(pt, Dg, nd * G);
+    }
+    D = Dg + static_cast<size_t>(i % G) * nd * dw;
+    if (pair && fuse_tail) {
+      // corr_mac and intt_moddown in one launch (RotTailBody): they are independent and overlap
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        RotTailBody<LOGV> body{
+            Corr0MacHalfBody<LOGV>{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), 2, c1n},
+            InvClusterBody<LOGV, PlanModDownGalois>{PlanModDownGalois{acc, nullptr, g1, e1, P_.logn}, dC_, twref(), pf_limbs_, static_cast<int>(nb * L)},
+            static_cast<int>(nb * L * 4)};
+        dev_.launch_cluster2(body, nb * L * 6, half_threads(LOGV), half_smem(LOGV));
+      });
+      std::swap(c0_in, c0_out);
+      continue;
+    }
     if (cluster_inv_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
         using Body = InvClusterBody<LOGV, PlanModDownGalois>;
@@ -100,12 +126,10 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
         dev_.launch(body, nb * L, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
     }
-    encode_material(mat, nullptr, kDiag, layer, i, pt, nd);
-    lift_ntt(pt, D, nd);
     if (half_fwd_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
         Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), pair ? 2 : 1, c1n};
-        dev_.launch(body, nb * L * (pair ? 4 : 2), half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
+        dev_.launch(body, nb * L * (pair ? 4 : 2), half_threads(LOGV), half_smem(LOGV));
       });
     } else {
       HHE_DISPATCH_LOG(P_.logn, {
@@ -138,7 +162,7 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_
   for (int k = 0; k < N2; ++k) {
     // the 16 diagonals of this giant step are encoded, lifted and transformed as one batch ([j][nd] items), then one pass over
     // the baby rotations forms the inner sum: every residue of `inner` is written once
-    for (int j = 0; j < N1; ++j) encode_material(mat, nullptr, kDiagBsgs, layer, k * N1 + j, pt + static_cast<size_t>(j) * nd * N, nd);
+    encode_material(mat, nullptr, kDiagBsgs, layer, k * N1, pt, nd, N1);  // [j][nd][N]
     lift_ntt(pt, D, nd * N1);
     DyadicMacNBody mac{rot, D, inner, dC_, N1, nb * ctw, nd * dw, dw, didx, nb * ctw};
     dev_.launch(mac, ew_grid(nb * ctw), kEwThreads, 0);

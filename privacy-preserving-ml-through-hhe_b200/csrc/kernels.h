@@ -89,12 +89,14 @@ constexpr int kKsFold1 = 6, kKsFold2 = 9, kKsOut16 = 64;
 struct RawU64 {
   const u64 *src;
   HD u64 raw(int i) const { return src[i]; }
+  HD const u64 *ptr(int i) const { return src + i; }
   HD double cvt(u64 v) const { return u_to_f(v); }
 };
 struct RawLift {  // centred lift of a plaintext coefficient into the limb (Evaluator::multiply_plain)
   const u64 *src;
   u64 thr, inc;
   HD u64 raw(int i) const { return src[i]; }
+  HD const u64 *ptr(int i) const { return src + i; }
   HD double cvt(u64 m) const { return u_to_f(m >= thr ? m + inc : m); }
 };
 struct RawCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[special] + half mod q_sp  (Corr0Mac)
@@ -102,6 +104,7 @@ struct RawCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[speci
   u64 half_sp, half_i, q;
   DevMod mi, msp;
   HD u64 raw(int j) const { return sp[j]; }
+  HD const u64 *ptr(int j) const { return sp + j; }
   HD double cvt(u64 v) const {
     const u64 r = csub(v + half_sp, msp.q);
     // r < q_sp: no reduction when q_sp <= q_i, one conditional subtraction when q_sp < 2 q_i (every BFVDefault set: the primes of a
@@ -565,6 +568,7 @@ struct KsDigitsTmemBody {
     u32 *tslot = reinterpret_cast<u32 *>(fm + ntt_smem_words(S));
     double *emu = fm + ntt_smem_words(S) + 2;
     (void)emu;
+
     const double q = C->qf[k], qi = C->qinvf[k];
     const F64Tw twk = tw.fwd_f(k);
     constexpr bool kFold = NttSchedule<LOGH>::kFirst == 1;
@@ -659,6 +663,88 @@ struct KsDigitsTmemBody {
     constexpr int G = (1 << LOGH) / 8;
     const MacIO io{k0, k1, G, nt, gpt * 2, q, qi, tbase, emu};
     fwd_half_passes_f64<LOGH, MacIO, kKsOut16, MAXT>(fm, twk, q, qi, h, nt, io);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// Key-switch digit kernel for SERVICE-SIZED requests (a handful of ciphertexts): the digit loop spread over a thread-block
+// cluster. With one ciphertext the kernel above keeps only 2K = 18 CTAs busy, each walking its L = 8 digits one after the other
+// (80 us per key switch at N = 16384, 518 of them per PASTA block). Here a cluster of 8 CTAs serves one (item, key limb, half):
+// CTA r transforms digit r and multiplies it with its key slice into shared-memory partial products; after a cluster barrier
+// every CTA sums one eighth of the residues over the 8 partial products through distributed shared memory and writes it out.
+// Same arithmetic, same result (exact integer sums in doubles), one digit's latency instead of eight. FP64 path, L <= 8.
+constexpr int kKsSplitCluster = 8;
+template <int LOGH>
+struct KsDigitsSplitBody {
+  static constexpr const char *kName = "ks_digits_split";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 1;
+  const u64 *target;
+  size_t stride;
+  const double *key;  // group-major FP64 key [L][2][K][N] (as KsDigitsTmemBody)
+  u64 *acc;           // [count][2][K][N], NTT form, canonical
+  const DevConsts *C;
+  TwRef tw;
+  const u64 *reuse;
+  size_t reuse_stride;
+  const u32 *perm;
+  static constexpr size_t smem_bytes() { return (ntt_smem_words(1 << LOGH) + 2 * (static_cast<size_t>(1) << LOGH)) * 8; }
+  HD void phase1(int bid, int, unsigned char *smem) const {
+    constexpr int nt = half_threads(LOGH);
+    constexpr int S = 1 << LOGH, G = S / 8;
+    const int N = 2 * S, K = C->K, L = C->L;
+    const int J = bid % kKsSplitCluster, u = bid / kKsSplitCluster;
+    const int b = u / (2 * K), kh = u % (2 * K), k = kh >> 1, h = kh & 1;
+    double *fm = reinterpret_cast<double *>(smem);
+    double *part = fm + ntt_smem_words(S);  // [2][S], group-major like the key: residue 8g+e at e*G+g
+    const double q = C->qf[k], qi = C->qinvf[k];
+    if (J >= L) {
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < 2 * S; i += nt) part[i] = 0.0;
+      }
+      return;
+    }
+    if (reuse && J == k) {  // NTT_J(target_J) is the permuted NTT of the source polynomial
+      const u64 *rn = reuse + static_cast<size_t>(b) * reuse_stride + static_cast<size_t>(J) * N;
+      const u32 *pm = perm + static_cast<size_t>(h) * S;
+      FOR_THREADS(tid, nt) {
+        for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(rn[pm[i]]);
+      }
+      SYNC();
+    } else {
+      const F64Tw twk = tw.fwd_f(k);
+      fwd_half_load_f64<LOGH>(fm, twk, q, qi, h, nt, RawU64{target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N});
+      fwd_half_passes_f64<LOGH, SmemIO, kKsOut16>(fm, twk, q, qi, h, nt);
+    }
+    const double *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
+    const double *k1 = k0 + static_cast<size_t>(K) * N;
+    FOR_THREADS(tid, nt) {
+      for (int idx = tid; idx < S; idx += nt) {
+        const int e = idx / G, g = idx % G;
+        const double v = fm[pidx(8 * g + e)];
+        part[idx] = f_mulmod_var(v, k0[idx], q, qi);      // |.| <= 1.25 q
+        part[S + idx] = f_mulmod_var(v, k1[idx], q, qi);
+      }
+    }
+  }
+  // peers[r]: shared memory of cluster rank r (own memory included)
+  HD void phase2(int bid, int, unsigned char *const *peers) const {
+    constexpr int nt = half_threads(LOGH);
+    constexpr int S = 1 << LOGH, G = S / 8, W = S / kKsSplitCluster;
+    const int N = 2 * S, K = C->K;
+    const int r = bid % kKsSplitCluster, u = bid / kKsSplitCluster;
+    const int b = u / (2 * K), kh = u % (2 * K), k = kh >> 1, h = kh & 1;
+    const double q = C->qf[k], qi = C->qinvf[k];
+    FOR_THREADS(tid, nt) {
+      for (int t = tid; t < 2 * W; t += nt) {
+        const int comp = t / W, idx = r * W + t % W;  // group-major index of this CTA's slice
+        double sum = 0.0;
+#pragma unroll
+        for (int p = 0; p < kKsSplitCluster; ++p)
+          sum = f_add(sum, (reinterpret_cast<const double *>(peers[p]) + ntt_smem_words(S))[comp * S + idx]);  // <= 10 q: exact
+        const int e = idx / G, g = idx % G;
+        acc[((static_cast<size_t>(b) * 2 + comp) * K + k) * N + static_cast<size_t>(h) * S + 8 * g + e] = f_canonical(sum, q, qi);
+      }
+    }
   }
 };
 
@@ -1001,10 +1087,12 @@ struct EncodeBody {
   u64 *pt;  // [items][N]
   const DevConsts *C;
   TwRef tw;
-  int mode, layer, diag;
+  int mode, layer, diag0;
+  int per;  // kDiag / kDiagBsgs: plaintexts per diagonal (item = g * per + m encodes diagonal diag0 + g from material row m); 0: one diagonal
   HD void operator()(int bid, int nt, unsigned char *smem) const {
     constexpr int S = 1 << LOGS;
     constexpr int T = kPastaT;
+    const int diag = diag0 + (per ? bid / per : 0), mrow = per ? bid % per : bid;
     u64 *sm = reinterpret_cast<u64 *>(smem);
     const int tab = 2 * C->K;
     const u64 t = C->t;
@@ -1013,7 +1101,7 @@ struct EncodeBody {
       for (int i = tid; i < S; i += nt) sm[pidx(i)] = 0;
     }
     SYNC();
-    const u32 *mat = material ? material + static_cast<size_t>(mat_index ? mat_index[bid] : bid) * kMaterialWords : nullptr;
+    const u32 *mat = material ? material + static_cast<size_t>(mat_index ? mat_index[mrow] : mrow) * kMaterialWords : nullptr;
     FOR_THREADS(tid, nt) {
       if (mode == kSlots) {
         const u32 cnt = lens ? lens[bid] : n;
@@ -1911,6 +1999,28 @@ struct PlanModDownAdd {  // InttModDownAddBody
     return StoreModDownAdd{acc + ((item * 2 + c) * K + (K - 1)) * N, bs ? bs + item * bstride + static_cast<size_t>(i) * N : nullptr,
                            out + ((item * 2 + c) * L + i) * N, C->n_inv_f[i], C->inv_sp_f[i], C->qf[i], C->qinvf[i], C->qf[K - 1],
                            static_cast<double>(C->half_sp), static_cast<double>(C->half_sp_mod_q[i])};
+  }
+};
+
+// The two kernels that finish a rotation of the resident chain -- corr_mac (both NTT-resident components + plaintext products) and
+// intt_moddown (component 1 back to coefficient form, ModDown, next Galois map) -- read the same key-switch accumulators and do
+// not depend on each other: one launch runs both (CTA pairs [0, n_corr) are corr_mac's, the rest intt_moddown's two-CTA clusters),
+// so they overlap instead of running back to back and a rotation is three launches (ks_digits, special-limb INTT, this).
+template <int LOGH>
+struct RotTailBody {
+  static constexpr const char *kName = "rot_tail";
+  static constexpr int kMaxThreads = 512, kMinBlocks = 2;
+  Corr0MacHalfBody<LOGH> corr;
+  InvClusterBody<LOGH, PlanModDownGalois> inv;
+  int n_corr;  // even
+  HD void phase1(int bid, int nt, unsigned char *smem) const {
+    if (bid < n_corr)
+      corr(bid, nt, smem);
+    else
+      inv.phase1(bid - n_corr, nt, smem);
+  }
+  HD void phase2(int bid, int nt, const unsigned char *smem, const unsigned char *peer) const {
+    if (bid >= n_corr) inv.phase2(bid - n_corr, nt, smem, peer);
   }
 };
 

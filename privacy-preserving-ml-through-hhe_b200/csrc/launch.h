@@ -82,6 +82,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BodyBounds<Body>::kT
   else if (BodyPeerSmem<Body>::value)
     cluster_sync_relaxed();  // the partner may still be reading this CTA's shared memory
 }
+
+// Eight-CTA cluster (portable maximum): phase1 on the CTA's own shared memory, a release/acquire cluster barrier, phase2 with the
+// shared-memory base of every rank (distributed shared memory, read-only), closing barrier so no CTA exits while it is being read.
+template <class Body>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry_c8(const Body body) {
+  extern __shared__ __align__(16) unsigned char hhe_smem[];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  body.phase1(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
+  cluster.sync();
+  unsigned char *peers[8];
+#pragma unroll
+  for (unsigned r = 0; r < 8; ++r) peers[r] = cluster.map_shared_rank(hhe_smem, r);
+  body.phase2(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), peers);
+  cluster_sync_relaxed();
+}
 #endif
 
 // Per-kernel device-time accounting (hhe_profile_*): when enabled every launch is bracketed by CUDA events on the
@@ -312,6 +328,52 @@ struct Device {
 #else
     std::vector<unsigned char> smem(smem_bytes + 16);
     for (size_t b = 0; b < grid; ++b) body(static_cast<int>(b), nt, smem.data());
+#endif
+  }
+
+  // grid must be a multiple of 8: CTAs 8p .. 8p+7 form a cluster (see kernel_entry_c8)
+  template <class Body>
+  void launch_cluster8(const Body &body, size_t grid, int nt, size_t smem_bytes) {
+    if (grid == 0) return;
+    if (grid & 7) throw std::invalid_argument("cluster launch needs a grid that is a multiple of 8");
+    ++launches;
+    int kid = -1;
+    if (profiling) {
+      kid = kernel_id(Body::kName);
+      ++stats[kid].launches;
+    }
+#ifdef HHE_CUDA
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    if (profiling) {
+      ev_a = get_event();
+      ev_b = get_event();
+      cuda_check(cudaEventRecord(ev_a, stream), "cudaEventRecord");
+    }
+    if (smem_bytes > 48 * 1024) {
+      static size_t configured[kMaxDevices] = {};  // per Body instantiation and device
+      size_t &conf = configured[ordinal & (kMaxDevices - 1)];
+      if (smem_bytes > conf) {
+        cuda_check(cudaFuncSetAttribute(kernel_entry_c8<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem_bytes)),
+                   "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        conf = smem_bytes;
+      }
+    }
+    kernel_entry_c8<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
+    cuda_check(cudaGetLastError(), "cluster-8 kernel launch");
+    if (profiling) {
+      cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
+      pending.push_back(Pending{kid, ev_a, ev_b});
+      if (pending.size() >= 8192) profile_resolve();
+    }
+#else
+    std::vector<std::vector<unsigned char>> sm(8, std::vector<unsigned char>(smem_bytes + 16));
+    unsigned char *peers[8];
+    for (int r = 0; r < 8; ++r) peers[r] = sm[r].data();
+    for (size_t b = 0; b < grid; b += 8) {
+      for (int r = 0; r < 8; ++r) body.phase1(static_cast<int>(b + r), nt, peers[r]);
+      for (int r = 0; r < 8; ++r) body.phase2(static_cast<int>(b + r), nt, peers);
+    }
 #endif
   }
 
