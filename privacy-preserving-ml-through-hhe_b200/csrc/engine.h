@@ -114,7 +114,7 @@ class Engine {
   bool compact_keys_ = false;
   bool tmem_ks_ = false;  // FP64 key switch with accumulators in tensor memory (keys stored group-major)
   size_t half_smem(int logh) const { return ntt_smem_words(1 << logh) * 8; }  // dynamic shared memory of a half-limb kernel
-  int ks_split_max_ = 4;   // up to this many items a key switch runs as eight-CTA clusters, one digit per CTA (HHE_KS_SPLIT_MAX)
+  int ks_split_max_ = 3;   // up to this many items (measured: 1-3 blocks faster, 4 slower than the standard kernel) a key switch runs as eight-CTA clusters, one digit per CTA (HHE_KS_SPLIT_MAX)
   int ks_threads_ = 512;   // CTA size of the tensor-memory key-switch kernel (512 x 64 registers or 256 x 128 registers)
   bool cluster_inv_ = false;  // FP64 inverse transforms as two-CTA clusters (half-limb CTAs, last stage over distributed shared memory)
   int pf_ntt_ = 0, pf_limbs_ = 0, pf_items_ = 0;  // L2 prefetch distances (limbs: plain transforms / other half-limb kernels; items: ks_digits); 0 = off

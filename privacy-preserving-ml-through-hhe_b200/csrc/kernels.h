@@ -718,11 +718,27 @@ struct KsDigitsSplitBody {
     const double *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
     const double *k1 = k0 + static_cast<size_t>(K) * N;
     FOR_THREADS(tid, nt) {
-      for (int idx = tid; idx < S; idx += nt) {
-        const int e = idx / G, g = idx % G;
-        const double v = fm[pidx(8 * g + e)];
-        part[idx] = f_mulmod_var(v, k0[idx], q, qi);      // |.| <= 1.25 q
-        part[S + idx] = f_mulmod_var(v, k1[idx], q, qi);
+      // one CTA per SM here (128 registers per thread): the key values of U residues are requested before the first product, so the
+      // multiply-accumulate costs S / (nt U) L2 round trips instead of S / nt
+      constexpr int U = 8;
+      for (int i0 = tid; i0 < S; i0 += nt * U) {
+        double ka[U], kb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = i0 + u * nt < S ? i0 + u * nt : i0;
+          ka[u] = k0[idx];
+          kb[u] = k1[idx];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int idx = i0 + u * nt;
+          if (idx < S) {
+            const int e = idx / G, g = idx % G;
+            const double v = fm[pidx(8 * g + e)];
+            part[idx] = f_mulmod_var(v, ka[u], q, qi);  // |.| <= 1.25 q
+            part[S + idx] = f_mulmod_var(v, kb[u], q, qi);
+          }
+        }
       }
     }
   }
@@ -737,10 +753,12 @@ struct KsDigitsSplitBody {
     FOR_THREADS(tid, nt) {
       for (int t = tid; t < 2 * W; t += nt) {
         const int comp = t / W, idx = r * W + t % W;  // group-major index of this CTA's slice
-        double sum = 0.0;
+        double term[kKsSplitCluster], sum = 0.0;
 #pragma unroll
-        for (int p = 0; p < kKsSplitCluster; ++p)
-          sum = f_add(sum, (reinterpret_cast<const double *>(peers[p]) + ntt_smem_words(S))[comp * S + idx]);  // <= 10 q: exact
+        for (int p = 0; p < kKsSplitCluster; ++p)  // the eight distributed-shared-memory loads first, then the sum
+          term[p] = (reinterpret_cast<const double *>(peers[p]) + ntt_smem_words(S))[comp * S + idx];
+#pragma unroll
+        for (int p = 0; p < kKsSplitCluster; ++p) sum = f_add(sum, term[p]);  // <= 10 q: exact
         const int e = idx / G, g = idx % G;
         acc[((static_cast<size_t>(b) * 2 + comp) * K + k) * N + static_cast<size_t>(h) * S + 8 * g + e] = f_canonical(sum, q, qi);
       }

@@ -11,7 +11,7 @@ for r in rows:
     m = re.search(r"<(?:hhe::)?(\w+)", name)
     key = m.group(1) if m and "kernel_entry" in name else name[:40]
     if "kernel_entry" in name:
-        key = re.sub(r"^void kernel_entry(_c2)?<(hhe::)?", "", name).split("(T1)")[0].rstrip(">")[:60]
+        key = re.sub(r"^void kernel_entry(_c2|_c8)?<(hhe::)?", "", name).split("(T1)")[0].rstrip(">")[:60]
     a = agg.setdefault(key, [0, 0.0])
     a[0] += 1
     a[1] += float(r[14]) / 1e3
