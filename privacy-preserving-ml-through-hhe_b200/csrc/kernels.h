@@ -132,6 +132,40 @@ HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int
       const int first = WARP_LOCAL ? ((tid >> 5) << 8) + (tid & 31) : tid;
       const int step = WARP_LOCAL ? 32 : nt;
       const int count = WARP_LOCAL ? 8 : (S / 2 - tid + nt - 1) / nt;
+      if constexpr (WARP_LOCAL) {
+      // ks_digits: loads two iterations ahead (8 more registers, still 64 without spills: ks_digits -1.4 %; the other users of this
+      // loader spill with it and lose 2 %, so they keep the one-iteration pipeline below; profiles/r2_ab_twiddle_pipeline.txt)
+      u64 v[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0}, nn[4] = {0, 0, 0, 0};
+      if (count > 0) {
+        v[0] = ld.raw(first);
+        v[1] = ld.raw(first + S);
+        v[2] = ld.raw(first + S / 2);
+        v[3] = ld.raw(first + S / 2 + S);
+      }
+      if (count > 1) {
+        nv[0] = ld.raw(first + step);
+        nv[1] = ld.raw(first + step + S);
+        nv[2] = ld.raw(first + step + S / 2);
+        nv[3] = ld.raw(first + step + S / 2 + S);
+      }
+      for (int k = 0; k < count; ++k) {
+        const int i = first + k * step, in = i + 2 * step;
+        if (k + 2 < count) {
+          nn[0] = ld.raw(in);
+          nn[1] = ld.raw(in + S);
+          nn[2] = ld.raw(in + S / 2);
+          nn[3] = ld.raw(in + S / 2 + S);
+        }
+        const double t0 = f_mulmod_const(ld.cvt(v[1]), w1, q), t1 = f_mulmod_const(ld.cvt(v[3]), w1, q);
+        const double a0 = h ? f_add(ld.cvt(v[0]), -t0) : f_add(ld.cvt(v[0]), t0);  // |.| <= 2.94q
+        const double a1 = h ? f_add(ld.cvt(v[2]), -t1) : f_add(ld.cvt(v[2]), t1);
+        const double tt = f_mulmod_const(a1, w2, q);
+        fm[pidx(i)] = f_add(a0, tt);  // |.| <= 4.1q
+        fm[pidx(i + S / 2)] = f_add(a0, -tt);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = nv[e], nv[e] = nn[e];
+      }
+      } else {
       u64 v[4] = {0, 0, 0, 0}, nv[4] = {0, 0, 0, 0};
       if (count > 0) {
         v[0] = ld.raw(first);
@@ -155,6 +189,7 @@ HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int
         fm[pidx(i + S / 2)] = f_add(a0, -tt);
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = nv[e];
+      }
       }
     }
   } else {
