@@ -268,7 +268,7 @@ def main():
     checked = "skipped (oracle/_ref absent: random key material)"
     for s in range(args.warmup):
         device_step(s)
-        if s == 0 and rank == 0 and ref is not None:
+        if s == 0 and rank == 0 and ref is not None and not os.environ.get("HHE_BENCH_NO_VERIFY"):  # (timing-only kernel experiments)
             ctx.sync()
             from oracle import oracle as O
             got = d_out[0].cpu().numpy().view(np.uint64)
