@@ -456,6 +456,22 @@ def main():
             gather_info = {"ciphertexts": world * B, "bytes_received_by_rank0": nbytes, "ms": float(g_ms.item()),
                            "GBps": nbytes / float(g_ms.item()) / 1e6, "rank0_block0_matches": bool(torch.equal(got[0], d_out[0]))}
         del got
+    # ---- BASELINE configs[4] at N GPUs: the primitive sweep is replicated (every rank runs independent batches of the same shape on
+    # its own GPU, no communication); rates are summed over the ranks. At one GPU the sweep is part of `configs` below. ----
+    sweep_agg = None
+    if world > 1 and not args.no_configs:
+        from tools import bench_configs as BC
+        barrier()
+        loc = BC.config5(stream, peak_hbm()[0], None, sizes=(8192, 16384, 32768))
+        names = [(n, op, f) for n in sorted(loc) for op, f in (("ntt_fwd", "GBps"), ("ntt_inv", "GBps"), ("rotate_rows", "per_s"),
+                                                                ("relinearize", "per_s"), ("multiply", "per_s"))]
+        vals = torch.tensor([loc[n][op][f] for n, op, f in names], dtype=torch.float64, device="cuda")
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            sweep_agg = {"ranks": world, "scaling": "weak (replicated batches, rates summed over ranks)"}
+            for (n, op, f), v in zip(names, vals.tolist()):
+                sweep_agg.setdefault(n, {})[f"{op}_{f}"] = v
+                sweep_agg[n][f"{op}_{f}_rank0"] = loc[n][op][f]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -571,7 +587,7 @@ def main():
                         "inside); `value`'s timed region additionally records two CUDA events per kernel launch for the live per-kernel "
                         "table (about 1 %), which is why e2e can come out marginally above it"},
         "gpu_launches": int(launches), "clocks": clocks, "verified": checked, "ntt": ntt_info, "gather": gather_info,
-        "sharding_invariance": invariance, "strong": strong, "fc": fc, "configs": configs,
+        "sharding_invariance": invariance, "strong": strong, "fc": fc, "configs": configs, "primitive_sweep_all_ranks": sweep_agg,
     }
     emit(out)
 

@@ -102,7 +102,6 @@ class Engine {
   void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
   void feistel(u64 *state, size_t nb);
   const W2 *need_key(int kind, u32 elt) const;
-  void require_whole_limb(const char *what) const;
   const u64 *feistel_mask_ntt();
 
   Params P_;

@@ -57,10 +57,6 @@ void Engine::ntt(const u64 *in, u64 *out, size_t items, int limbs, const TabMap 
   });
 }
 
-void Engine::require_whole_limb(const char *what) const {
-  if (split_) throw std::invalid_argument(std::string(what) + " is not available at poly_modulus_degree 32768 in this build (NTT, rotate, relinearize, multiply are)");
-}
-
 void Engine::add(const u64 *a, const u64 *b, u64 *out, size_t items, int size) {
   const size_t total = items * ct_words(size);
   AddBody body{a, b, out, dC_, size * P_.L, total};
@@ -86,7 +82,14 @@ void Engine::broadcast(const u64 *src, u64 *out, size_t words, size_t items) {
 
 void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items) {
   if (n > P_.N) throw std::invalid_argument("values_matrix size exceeds slot count");
-  require_whole_limb("encode");
+  if (split_) {  // N = 32768: slot vector in global memory, then the split inverse transform mod t
+    EncodeScatterBody body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, kSlots, 0, 0, 0};
+    dev_.launch(body, items, 256, 0);
+    TabMap mt{};
+    mt.id[0] = static_cast<unsigned char>(P_.tab_plain());
+    ntt(pt, pt, items, 1, mt, true);
+    return;
+  }
   HHE_DISPATCH_LOG(P_.logn, {
     EncodeBody<LOGV> body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, twref(), kSlots, 0, 0, 0};
     dev_.launch(body, items, ntt_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
@@ -94,7 +97,15 @@ void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32
 }
 
 void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items, int ndiag) {
-  require_whole_limb("PASTA transciphering");
+  if (split_) {
+    const size_t all = items * static_cast<size_t>(ndiag > 1 ? ndiag : 1);
+    EncodeScatterBody body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, mode, layer, diag, ndiag > 1 ? static_cast<int>(items) : 0};
+    dev_.launch(body, all, 256, 0);
+    TabMap mt{};
+    mt.id[0] = static_cast<unsigned char>(P_.tab_plain());
+    ntt(pt, pt, all, 1, mt, true);
+    return;
+  }
   HHE_DISPATCH_LOG(P_.logn, {
     EncodeBody<LOGV> body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, twref(), mode, layer, diag,
                           ndiag > 1 ? static_cast<int>(items) : 0};
@@ -103,7 +114,15 @@ void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode
 }
 
 void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items, const u32 *nolift) {
-  require_whole_limb("multiply_plain");
+  if (split_) {  // N = 32768: element-wise lift, then split forward transforms (out of place: D is written by the lift first)
+    Scope sc(*this);
+    const size_t total = items * P_.L * P_.N;
+    u64 *lifted = scratch(total);
+    LiftBody body{pt, lifted, dC_, nolift, total};
+    dev_.launch(body, ew_grid(total), kEwThreads, 0);
+    ntt(lifted, D, items, P_.L, map_mod(P_.L, P_.L, 0), false);
+    return;
+  }
   if (half_fwd_) {
     HHE_DISPATCH_LOG(P_.logn - 1, {
       LiftNttHalfBody<LOGV> body{pt, D, dC_, twref(), nolift};
@@ -119,7 +138,15 @@ void Engine::lift_ntt(const u64 *pt, u64 *D, size_t items, const u32 *nolift) {
 
 void Engine::ntt_mac(const u64 *ct, const u64 *D, size_t dstride, u64 *sum, size_t items, bool first, int comps, size_t sum_off,
                      u64 *ntt_out, const u32 *didx) {
-  require_whole_limb("multiply_plain");
+  if (split_) {  // N = 32768: split forward transforms of the ciphertext limbs, then the element-wise product and sum
+    Scope sc(*this);
+    const size_t total = items * comps * P_.L * P_.N;
+    u64 *xn = ntt_out ? ntt_out : scratch(total);
+    ntt(ct, xn, items, comps * P_.L, map_mod(comps * P_.L, P_.L, 0), false);
+    DyadicMacBody body{xn, D, dstride, sum, dC_, first ? 1 : 0, comps, ct_words(), sum_off, didx, total};
+    dev_.launch(body, ew_grid(total), kEwThreads, 0);
+    return;
+  }
   if (half_fwd_) {
     HHE_DISPATCH_LOG(P_.logn - 1, {
       NttMacHalfBody<LOGV> body{ct, D, dstride, sum, dC_, twref(), first ? 1 : 0, comps, ct_words(), sum_off, ntt_out, didx,

@@ -1196,6 +1196,112 @@ struct EncodeBody {
 };
 
 // ------------------------------------------------------------------------------------------------------------
+// N = 32768 (split transforms): the whole-limb kernels encode / lift_ntt / ntt_mac as element-wise pieces around Engine::ntt.
+// EncodeScatterBody builds the slot vector of EncodeBody in global memory (the inverse NTT mod t follows as a split transform);
+// LiftBody is the centred lift of multiply_plain into every limb; DyadicMacBody the product with the lifted diagonal and the sum.
+struct EncodeScatterBody {
+  static constexpr const char *kName = "encode";
+  const u64 *slots;
+  size_t sstride;
+  const u32 *lens;
+  u32 n;
+  const u32 *material;
+  const u32 *mat_index;
+  const u32 *index_map;
+  u64 *pt;  // [items][N]: slot values at their index_map positions, zero elsewhere
+  const DevConsts *C;
+  int mode, layer, diag0, per;
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    constexpr int T = kPastaT;
+    const size_t N = C->N;
+    const int half = static_cast<int>(N / 2);
+    const int diag = diag0 + (per ? bid / per : 0), mrow = per ? bid % per : bid;
+    u64 *dst = pt + static_cast<size_t>(bid) * N;
+    FOR_THREADS(tid, nt) {
+      for (size_t i = tid; i < N; i += nt) dst[i] = 0;
+    }
+    SYNC();
+    const u32 *mat = material ? material + static_cast<size_t>(mat_index ? mat_index[mrow] : mrow) * kMaterialWords : nullptr;
+    FOR_THREADS(tid, nt) {
+      if (mode == kSlots) {
+        const u32 cnt = lens ? lens[bid] : n;
+        for (u32 i = tid; i < cnt; i += nt) dst[index_map[i]] = slots[static_cast<size_t>(bid) * sstride + i];
+      } else if (mode == kRc) {
+        for (int i = tid; i < 2 * T; i += nt) dst[index_map[i < T ? i : half + (i - T)]] = mat[kMatWords + layer * 2 * T + i];
+      } else if (mode == kFeistel) {
+        for (int i = tid; i < 2 * T; i += nt) {
+          const int j = i & (T - 1);
+          if (j) dst[index_map[(i < T ? 0 : half) + j]] = 1;
+        }
+      } else {
+        for (int i = tid; i < 2 * T; i += nt) {
+          const int which = i >= T, p = i & (T - 1);
+          const u32 *M = mat + (static_cast<size_t>(layer) * 2 + which) * T * T;
+          int slot = p, src = p;
+          if (mode == kDiagBsgs) {
+            const int shift = (diag / 16) * 16;
+            src = (p + shift) & (T - 1);
+            if (half != T && p >= T - shift) slot = p + (half - T);
+          }
+          dst[index_map[which * half + slot]] = M[src * T + ((src + T - diag) & (T - 1))];
+        }
+      }
+    }
+  }
+};
+
+struct LiftBody {  // out[item][i][j] = centred lift of pt[item][j] into limb i (no lift for monomial plaintexts, see LiftNttBody)
+  static constexpr const char *kName = "lift";
+  const u64 *pt;  // [items][N]
+  u64 *out;       // [items][L][N]
+  const DevConsts *C;
+  const u32 *nolift;
+  size_t total;  // items * L * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    const u32 L = static_cast<u32>(C->L);
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const u32 limb = static_cast<u32>(g >> C->logn), i = limb % L, item = limb / L;
+        const u64 m = pt[static_cast<size_t>(item) * N + (g & (N - 1))];
+        const bool lift = m >= C->half_t && !(nolift && nolift[item]);
+        out[g] = lift ? m + (C->mod[i].q - C->t) : m;
+      }
+    }
+  }
+};
+
+struct DyadicMacBody {  // sum (+)= x (.) D   (x: NTT form [items][comps][L][N])
+  static constexpr const char *kName = "dyadic_mac1";
+  const u64 *x;
+  const u64 *D;
+  size_t dstride;
+  u64 *sum;
+  const DevConsts *C;
+  int first, comps;
+  size_t sum_stride, sum_off;
+  const u32 *didx;
+  size_t total;  // items * comps * L * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    const u32 L = static_cast<u32>(C->L);
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const u32 limb = static_cast<u32>(g >> C->logn), i = limb % L, cl = limb % (comps * L), item = limb / (comps * L);
+        const size_t j = g & (N - 1);
+        const DevMod mi = C->mod[i];
+        u64 v = mul_mod(x[g], D[(didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + j], mi);
+        u64 *dst = sum + static_cast<size_t>(item) * sum_stride + sum_off + static_cast<size_t>(cl) * N + j;
+        if (!first) v = add_mod(v, *dst, mi.q);
+        *dst = v;
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
 // Plaintext half of Evaluator::multiply_plain (seal/evaluator.h:729): centred lift of pt into limb i, forward NTT.
 // grid = items * L
 template <int LOGS>

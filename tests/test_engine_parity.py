@@ -325,8 +325,25 @@ def test_split_path_forced(backend, monkeypatch):
     m3 = orc.multiply(a, b)
     assert np.array_equal(ctx.multiply(a, b), m3)
     assert np.array_equal(ctx.relinearize(m3), orc.relinearize(m3))
-    with pytest.raises(pkg.HheInvalidArgument):
-        ctx.encode(np.arange(8, dtype=np.uint64))  # whole-limb kernels are not available on this path yet
+    # the whole-limb operations as split transforms + element-wise pieces (encode, multiply_plain incl. a monomial, mask) and a
+    # whole PASTA-3 block on this path (what N = 32768 runs)
+    sl = rng.integers(0, common.T, 300, dtype=np.uint64)
+    assert np.array_equal(ctx.encode(sl), orc.encode(sl))
+    pt = orc.encode(sl)
+    assert np.array_equal(ctx.multiply_plain(a, pt), orc.multiply_plain(a, pt))
+    mono = np.zeros(N, dtype=np.uint64)
+    mono[3] = common.T - 2
+    assert np.array_equal(ctx.multiply_plain(a, mono), orc.multiply_plain(a, mono))
+    assert np.array_equal(ctx.mask(a, np.ones(20, dtype=np.uint64)), orc.mask(a, np.ones(20, dtype=np.uint64)))
+    for s_ in (0, 128):
+        e = orc.galois_elt(s_)
+        k = keys.galois_key(e)
+        orc.load_ksk(0, e, k)
+        ctx.load_ksk(0, e, k)
+    key256 = rng.integers(0, common.T, 256, dtype=np.uint64)
+    enc_key = keys.encrypt_zero_plus(orc, orc.encode(common.pack_key(key256, N)))
+    sym = O.pasta_plain(key256, common.T, rng.integers(0, common.T, 128, dtype=np.uint64))
+    assert np.array_equal(ctx.pasta3_decompose(enc_key, sym), orc.pasta_decompose(enc_key, sym))
     ctx.close()
     orc.close()
 

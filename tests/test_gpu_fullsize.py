@@ -163,6 +163,32 @@ def test_n32768_primitives_bit_exact_with_seal():
     ref.close()
 
 
+def test_n32768_whole_path_bit_exact_with_seal():
+    """N = 32768 beyond the primitive sweep: encode, multiply_plain, mask and one whole PASTA-3 block (split transforms + element-wise
+    pieces, integer arithmetic: the 55/56-bit primes are outside the FP64 path) against the reference (~90 s of SEAL for the block)."""
+    NN = 32768
+    ref = R.Ref(NN, common.T, None, seed=16, steps=(0, -1, 128), default_gk=False)
+    ctx = pkg.Context(NN, common.T, ref.q, device=0)
+    common.load_keys_from_ref(ctx, ref, keysets=(0,))
+    rng = np.random.default_rng(19)
+    sl = rng.integers(0, common.T, 9000, dtype=np.uint64)
+    assert np.array_equal(ctx.encode(sl), ref.encode(sl))
+    a = ref.encrypt(rng.integers(0, common.T, NN, dtype=np.uint64))
+    pt = ref.encode(sl)
+    assert np.array_equal(ctx.multiply_plain(a, pt), ref.multiply_plain(a, pt))
+    assert np.array_equal(ctx.mask(a, np.ones(40, dtype=np.uint64)), ref.mask(a, np.ones(40, dtype=np.uint64)))
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    enc_key = ref.encrypt(common.pack_key(key, NN))
+    words = rng.integers(0, common.T, 128, dtype=np.uint64)
+    sym = O.pasta_plain(key, common.T, words)
+    got = ctx.pasta3_decompose(enc_key, sym)
+    assert np.array_equal(got, ref.pasta_decompose(enc_key, sym))
+    slots, budget = ref.decrypt(got[0])
+    assert budget > 100 and np.array_equal(slots[:128], words)
+    ctx.close()
+    ref.close()
+
+
 def test_n8192_primitives_bit_exact_with_seal():
     """BASELINE.json configs[4] at N=8192, BFVDefault (L=4 + special, 43/44-bit primes: FP64-pipe kernels)."""
     NN = 8192
