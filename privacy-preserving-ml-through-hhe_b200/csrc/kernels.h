@@ -236,6 +236,93 @@ HD void fwd_half_passes_f64(double *fm, F64Tw twk, double q, double qi, int h, i
     ntt_fwd_core_f64<LOGH, 1, kKsFold1, IO, MAXOUT16, NT>(fm, twk, q, qi, h, nt, io);
 }
 
+// Folded load + FIRST REGISTER PASS in one step (S = 16 nt, i.e. N = 16384 with 512 threads). Thread t's eight fold iterations
+// i = t + e S/16 (e = 0..7) produce the residues t + e S/16 and S/2 + t + e S/16: exactly the two radix-8 groups (element stride
+// S/16) that the same thread owns in the first register pass. So the fold's outputs never visit shared memory: the thread runs
+// the pass's three stages on them in registers and stores the pass's outputs. One shared-memory round trip (S doubles written and
+// read back, 14 % of the LSU wavefronts of a key-switch digit) and one barrier less per transform; the FP64 work is unchanged.
+// `before_store`: executed by every thread between its last global load and its first shared-memory store (the key-switch kernel
+// places the barrier there that protects the previous digit's last pass, which is still reading the buffer).
+constexpr bool half_fused_first_pass(int logh, int nt) {
+#if defined(HHE_NO_FUSED_FIRST_PASS)
+  return false && logh && nt;
+#else
+  return NttSchedule_first(logh) == 1 && nt * 16 == (1 << logh) && logh >= 7;
+#endif
+}
+
+template <int LOGH, class LD, class IO, int MAXOUT16, int MAXT, class PRE>
+HD void fwd_half_fused_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const LD &ld, const IO &io, const PRE &before_store) {
+  constexpr int S = 1 << LOGH;
+  constexpr int NT = half_threads(LOGH, MAXT);
+  static_assert(NttSchedule<LOGH>::kFirst == 1 && NT * 16 == S, "fused first pass: S = 16 nt and a single-stage odd pass");
+  using Pass1 = FwdChainF64<LOGH, 1, 1, kKsFold2 * 8, MAXOUT16, NT>;  // the pass being fused (local stages 1..3)
+  static_assert(Pass1::R == 3 && !Pass1::kLast, "fused first pass is a full radix-8 pass followed by others");
+  using Rest = FwdChainF64<LOGH, 1, 4, Pass1::kOut, MAXOUT16, NT>;
+  constexpr int LG = LOGH - 4;  // element stride of the pass: S/16 = NT
+  const D2 w1{twk.idx[1], f_mul(twk.idx[1], qi)};
+  const D2 w2{twk.idx[2 + h], f_mul(twk.idx[2 + h], qi)};
+  FOR_THREADS(tid, nt) {
+    double xa[8], xb[8];
+    u64 v[4], nv[4] = {0, 0, 0, 0};
+    v[0] = ld.raw(tid);
+    v[1] = ld.raw(tid + S);
+    v[2] = ld.raw(tid + S / 2);
+    v[3] = ld.raw(tid + S / 2 + S);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (e + 1 < 8) {
+        const int in = tid + (e + 1) * NT;
+        nv[0] = ld.raw(in);
+        nv[1] = ld.raw(in + S);
+        nv[2] = ld.raw(in + S / 2);
+        nv[3] = ld.raw(in + S / 2 + S);
+      }
+      const double t0 = f_mulmod_const(ld.cvt(v[1]), w1, q), t1 = f_mulmod_const(ld.cvt(v[3]), w1, q);
+      const double a0 = h ? f_add(ld.cvt(v[0]), -t0) : f_add(ld.cvt(v[0]), t0);  // |.| <= 2.94q
+      const double a1 = h ? f_add(ld.cvt(v[2]), -t1) : f_add(ld.cvt(v[2]), t1);
+      const double tt = f_mulmod_const(a1, w2, q);
+      xa[e] = f_add(a0, tt);  // residue tid + e NT          |.| <= 4.1q
+      xb[e] = f_add(a0, -tt);  // residue S/2 + tid + e NT
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = nv[c];
+    }
+    // the two groups of the first register pass: g = tid (block 0) and g = NT + tid (block 1), element stride NT
+    double wv[8];
+    group_tw_f64<3, LOGH, 1, 1>(twk, h, tid, wv);
+    group_math_f64<3, false, Pass1::kHalfMode ? kHalf : kNone>(xa, wv, q, qi);
+    group_tw_f64<3, LOGH, 1, 1>(twk, h, NT + tid, wv);
+    group_math_f64<3, false, Pass1::kHalfMode ? kHalf : kNone>(xb, wv, q, qi);
+    before_store();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      fm[pidx(tid + (e << LG))] = xa[e];
+      fm[pidx(S / 2 + tid + (e << LG))] = xb[e];
+    }
+  }
+  sync_domain<LG, NT>();  // as after the unfused pass: its element stride is the larger one
+  Rest::run(fm, twk, q, qi, h, nt, io);
+}
+
+struct NoPre {
+  HD void operator()() const {}
+};
+struct CtaBarrier {  // every thread of the CTA calls it (uniform control flow)
+  HD void operator()() const { SYNC(); }
+};
+
+// folded load + all register passes of a half-limb forward transform (fused first pass where the CTA shape allows it; FUSE = false
+// for loaders whose conversion needs too many registers next to the 16 residues: corr_mac's RawCorr spills and loses 2 %)
+template <int LOGH, class LD, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16, int MAXT = 512, bool FUSE = true>
+HD void fwd_half_transform_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const LD &ld, const IO &io = IO()) {
+  if constexpr (FUSE && half_fused_first_pass(LOGH, half_threads(LOGH, MAXT))) {
+    fwd_half_fused_f64<LOGH, LD, IO, MAXOUT16, MAXT>(fm, twk, q, qi, h, nt, ld, io, NoPre{});
+  } else {
+    fwd_half_load_f64<LOGH>(fm, twk, q, qi, h, nt, ld);
+    fwd_half_passes_f64<LOGH, IO, MAXOUT16, MAXT>(fm, twk, q, qi, h, nt, io);
+  }
+}
+
 constexpr int kMaxMapLimbs = 3 * kMaxLimbs;  // size-3 ciphertext in the Bsk base
 struct TabMap {  // limb index inside an item -> NTT table id
   unsigned char id[kMaxMapLimbs];
@@ -642,6 +729,13 @@ struct KsDigitsTmemBody {
         continue;
       }
       const u64 *dig = target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N;
+      if constexpr (half_fused_first_pass(LOGH, nt)) {
+        // folded load + first register pass in registers; the CTA barrier sits between a thread's last digit load and its first
+        // store, where it also covers the previous digit's last pass (other warps may still be reading the buffer)
+        const MacIO io{k0, k1, G, nt, gpt * 2, q, qi, tbase, emu};
+        fwd_half_fused_f64<LOGH, RawU64, MacIO, kKsOut16, MAXT>(fm, twk, q, qi, h, nt, RawU64{dig}, io, CtaBarrier{});
+        continue;
+      }
       fwd_half_load_f64<LOGH, RawU64, kWarpLocal>(fm, twk, q, qi, h, nt, RawU64{dig});  // ends with a barrier
       // register passes; the last one hands its outputs to KsMacOut::group_out. The functor is rebuilt per thread inside
       // the chain's FOR_THREADS through TmemAcc::make, so pass the ingredients.
@@ -747,8 +841,8 @@ struct KsDigitsSplitBody {
       SYNC();
     } else {
       const F64Tw twk = tw.fwd_f(k);
-      fwd_half_load_f64<LOGH>(fm, twk, q, qi, h, nt, RawU64{target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N});
-      fwd_half_passes_f64<LOGH, SmemIO, kKsOut16>(fm, twk, q, qi, h, nt);
+      fwd_half_transform_f64<LOGH, RawU64, SmemIO, kKsOut16>(fm, twk, q, qi, h, nt,
+                                                             RawU64{target + static_cast<size_t>(b) * stride + static_cast<size_t>(J) * N});
     }
     const double *k0 = key + ((static_cast<size_t>(J) * 2 + 0) * K + k) * N + static_cast<size_t>(h) * S;
     const double *k1 = k0 + static_cast<size_t>(K) * N;
@@ -1704,9 +1798,8 @@ struct LiftNttHalfBody {
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[i], qi = C->qinvf[i];
     const F64Tw twk = tw.fwd_f(i);
-    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt,
-                            RawLift{pt + item * (2 * S), (nolift && nolift[item]) ? ~static_cast<u64>(0) : C->half_t, q - C->t});
-    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
+    fwd_half_transform_f64<LOGH>(fm, twk, qd, qi, h, nt,
+                                 RawLift{pt + item * (2 * S), (nolift && nolift[item]) ? ~static_cast<u64>(0) : C->half_t, q - C->t});
     u64 *dst = out + static_cast<size_t>(lb) * (2 * S) + static_cast<size_t>(h) * S;
     FOR_THREADS(tid, nt) {
 #pragma unroll 4
@@ -1752,8 +1845,7 @@ struct NttMacHalfBody {
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[i], qi = C->qinvf[i];
     const F64Tw twk = tw.fwd_f(i);
-    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawU64{ct + static_cast<size_t>(lb) * (2 * S)});
-    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
+    fwd_half_transform_f64<LOGH>(fm, twk, qd, qi, h, nt, RawU64{ct + static_cast<size_t>(lb) * (2 * S)});
     FOR_THREADS(tid, nt) {
       constexpr int U = 4;
       for (int j0 = tid; j0 < S; j0 += nt * U) {
@@ -1830,8 +1922,8 @@ struct Corr0MacHalfBody {
     u64 *cout = (c ? c1_out : c0_out) + (item * L + i) * N + hoff;
     const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + hoff;
     u64 *s0 = sum + ((item * 2 + c) * L + i) * N + hoff;
-    fwd_half_load_f64<LOGH>(fm, twk, qd, qi, h, nt, RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
-    fwd_half_passes_f64<LOGH>(fm, twk, qd, qi, h, nt);
+    fwd_half_transform_f64<LOGH, RawCorr, SmemIO, kF64AnyOut16, 512, false>(fm, twk, qd, qi, h, nt,
+                                                                            RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
     const u32 *pm = perm + hoff;
     const D2 isp = C->inv_sp_f[i];
     FOR_THREADS(tid, nt) {
@@ -2081,7 +2173,8 @@ struct NttFwdClusterBody {
     const int h = bid & 1, lb = bid >> 1, tab = map.id[lb % limbs];
     if (pf && !h && lb + pf < nl) cta_prefetch_l2(in + at(lb + pf), sizeof(u64) << (LOGH + 1));
     double *fm = reinterpret_cast<double *>(smem);
-    fwd_half_load_f64<LOGH>(fm, tw.fwd_f(tab), C->qf[tab], C->qinvf[tab], h, nt, RawU64{in + at(lb)});
+    // every global read of the limb happens here (the cluster barrier that follows separates them from the in-place stores)
+    fwd_half_transform_f64<LOGH>(fm, tw.fwd_f(tab), C->qf[tab], C->qinvf[tab], h, nt, RawU64{in + at(lb)});
   }
   HD void phase2(int bid, int, unsigned char *smem, const unsigned char *) const {
     constexpr int nt = half_threads(LOGH);
@@ -2089,7 +2182,6 @@ struct NttFwdClusterBody {
     const int h = bid & 1, lb = bid >> 1, tab = map.id[lb % limbs];
     double *fm = reinterpret_cast<double *>(smem);
     const double qd = C->qf[tab], qi = C->qinvf[tab];
-    fwd_half_passes_f64<LOGH>(fm, tw.fwd_f(tab), qd, qi, h, nt);
     u64 *dst = out + at(lb) + static_cast<size_t>(h) * S;
     FOR_THREADS(tid, nt) {
 #pragma unroll 4

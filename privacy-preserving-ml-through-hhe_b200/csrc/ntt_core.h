@@ -264,22 +264,10 @@ HD void group_tw_f64(F64Tw tw, int chunk, int g, double *wv) {
   }
 }
 
-// The butterflies of group g with its twiddles in wv (see group_tw_f64).
-template <int R, bool INVERSE, int LOGS, int S0, int LM, int MODE, class IO = SmemIO>
-HD void group_core_f64(double *sm, const double *wv, double q, double qinv, int g, const IO &io = IO()) {
+// The R butterfly stages of one radix-2^R group held in registers (x[0 .. 2^R)), twiddles in wv (see group_tw_f64).
+template <int R, bool INVERSE, int MODE>
+HD void group_math_f64(double *x, const double *wv, double q, double qinv) {
   constexpr int E = 1 << R;
-  constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
-  if (LG == 3) g = stride8_group(g);
-  const int lo = g & ((1 << LG) - 1), hi = g >> LG;
-  // padded shared-memory offsets: pidx(base + (e << LG)) = a0 + off(e) with compile-time off(e)
-  const int a0 = pidx(hi << (LOGS - S0)) + lo + (LG >= 4 ? (lo >> 4) : 0);
-  auto off = [](int e) constexpr { return LG >= 4 ? e * ((1 << LG) + (1 << (LG >= 4 ? LG - 4 : 0))) : (e << LG) + (e >> (LG < 4 ? 4 - LG : 0)); };
-  constexpr bool kGlobalIn = IO::kLoad && !INVERSE && S0 == 0;
-  constexpr bool kGlobalOut = IO::kStore && INVERSE && S0 == 0;
-  constexpr bool kGroupOut = IO::kGroupOut && !INVERSE && S0 + R == LOGS;
-  double x[E];
-#pragma unroll
-  for (int e = 0; e < E; ++e) x[e] = kGlobalIn ? io.load((hi << (LOGS - S0)) + lo + (e << LG)) : sm[a0 + off(e)];
   if (MODE == kFull) {
 #pragma unroll
     for (int e = 0; e < E; ++e) x[e] = f_reduce(x[e], q, qinv);
@@ -321,6 +309,26 @@ HD void group_core_f64(double *sm, const double *wv, double q, double qinv, int 
       }
     }
   }
+}
+
+// The butterflies of group g with its twiddles in wv: residues from shared memory (or IO::load), results to shared memory
+// (or IO::store / IO::group_out).
+template <int R, bool INVERSE, int LOGS, int S0, int LM, int MODE, class IO = SmemIO>
+HD void group_core_f64(double *sm, const double *wv, double q, double qinv, int g, const IO &io = IO()) {
+  constexpr int E = 1 << R;
+  constexpr int LG = LOGS - S0 - R;  // log2 of the element stride inside the group
+  if (LG == 3) g = stride8_group(g);
+  const int lo = g & ((1 << LG) - 1), hi = g >> LG;
+  // padded shared-memory offsets: pidx(base + (e << LG)) = a0 + off(e) with compile-time off(e)
+  const int a0 = pidx(hi << (LOGS - S0)) + lo + (LG >= 4 ? (lo >> 4) : 0);
+  auto off = [](int e) constexpr { return LG >= 4 ? e * ((1 << LG) + (1 << (LG >= 4 ? LG - 4 : 0))) : (e << LG) + (e >> (LG < 4 ? 4 - LG : 0)); };
+  constexpr bool kGlobalIn = IO::kLoad && !INVERSE && S0 == 0;
+  constexpr bool kGlobalOut = IO::kStore && INVERSE && S0 == 0;
+  constexpr bool kGroupOut = IO::kGroupOut && !INVERSE && S0 + R == LOGS;
+  double x[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) x[e] = kGlobalIn ? io.load((hi << (LOGS - S0)) + lo + (e << LG)) : sm[a0 + off(e)];
+  group_math_f64<R, INVERSE, MODE>(x, wv, q, qinv);
   if (kGroupOut) {
     io.group_out(g, x);
     return;

@@ -415,3 +415,32 @@ def test_plain_pasta3_matches_reference_kat_and_oracle(backend):
     with pytest.raises(pkg.HheInvalidArgument):
         ctx.pasta3_plain(key[:100], words)
     ctx.close()
+
+
+def test_fullsize_ring_on_the_emulation_harness():
+    """N = 16384 with the BFVDefault primes is the only shape where a half-limb CTA has S = 16 x 512 residues: the folded load fused with
+    the first register pass (kernels.h fwd_half_fused_f64) and the 512-thread tensor-memory key switch exist only there. The kernel
+    index arithmetic of that shape is checked here against the oracle (CPU tier); the B200 tests repeat it against SEAL."""
+    NN = 16384
+    q = common.Q_16384
+    orc = O.Oracle(NN, common.T, q)
+    ctx = make_ctx("emul", NN, q)
+    rng = np.random.default_rng(21)
+    for limb in (0, 4, 8):
+        x = rng.integers(0, int(q[limb]), NN, dtype=np.uint64)
+        f = ctx.ntt(limb, x)
+        assert np.array_equal(f, orc.ntt(limb, x)), limb
+        assert np.array_equal(ctx.ntt(limb, f, inverse=True), x), limb
+    keys = ToyKeys(orc, 5)
+    e1 = orc.galois_elt(-1)
+    k1 = keys.galois_key(e1)
+    orc.load_ksk(0, e1, k1)
+    ctx.load_ksk(0, e1, k1)
+    a = keys.encrypt_zero_plus(orc, orc.encode(rng.integers(0, common.T, 300, dtype=np.uint64)))
+    assert np.array_equal(ctx.rotate_rows(a, -1), orc.rotate_rows(a, -1))               # cluster-8 key switch (1 item)
+    five = np.stack([a] * 5)
+    assert np.array_equal(ctx.rotate_rows(five, -1)[4], orc.rotate_rows(a, -1))          # tensor-memory key switch (5 items)
+    pt = orc.encode(rng.integers(0, common.T, 500, dtype=np.uint64))
+    assert np.array_equal(ctx.multiply_plain(a, pt), orc.multiply_plain(a, pt))          # lift_ntt + ntt_mac
+    ctx.close()
+    orc.close()
