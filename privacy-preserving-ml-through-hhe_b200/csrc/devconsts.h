@@ -64,10 +64,12 @@ inline bool table_is_f64(const Params &p, int tab) {
   (void)p; (void)tab;
   return false;
 #else
-  if (tab >= p.K || p.L > 8) return false;
+  // the coefficient primes, and (round 2) the plain modulus: BatchEncoder::encode's inverse transform mod t then runs on the FP64
+  // half-limb cluster kernels as well (t = 65537 is far below the 2^49 limit)
+  if ((tab >= p.K && tab != p.tab_plain()) || p.L > 8) return false;
   for (int i = 0; i < p.K; ++i)
     if (p.q[i] >= kF64ModLimit) return false;
-  return true;
+  return tab < p.K || p.t < kF64ModLimit;
 #endif
 }
 

@@ -82,7 +82,9 @@ void Engine::broadcast(const u64 *src, u64 *out, size_t words, size_t items) {
 
 void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items) {
   if (n > P_.N) throw std::invalid_argument("values_matrix size exceeds slot count");
-  if (split_) {  // N = 32768: slot vector in global memory, then the split inverse transform mod t
+  if (split_ || table_is_f64(P_, P_.tab_plain())) {
+    // slot vector in global memory, then the inverse transform mod t as a batched NTT: split transforms at N = 32768, the FP64
+    // two-CTA cluster kernels when the ring is on the FP64 path (half the time of the whole-limb integer encode kernel)
     EncodeScatterBody body{slots, sstride, lens, n, nullptr, nullptr, dIndex_, pt, dC_, kSlots, 0, 0, 0};
     dev_.launch(body, items, 256, 0);
     TabMap mt{};
@@ -97,7 +99,7 @@ void Engine::encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32
 }
 
 void Engine::encode_material(const u32 *material, const u32 *mat_index, int mode, int layer, int diag, u64 *pt, size_t items, int ndiag) {
-  if (split_) {
+  if (split_ || table_is_f64(P_, P_.tab_plain())) {
     const size_t all = items * static_cast<size_t>(ndiag > 1 ? ndiag : 1);
     EncodeScatterBody body{nullptr, 0, nullptr, 0, material, mat_index, dIndex_, pt, dC_, mode, layer, diag, ndiag > 1 ? static_cast<int>(items) : 0};
     dev_.launch(body, all, 256, 0);
