@@ -43,6 +43,9 @@ Engine::Engine(const Params &p, int device, void *stream) : P_(p), device_(devic
   if (const char *v = std::getenv("HHE_KS_SPLIT_MAX")) ks_split_max_ = std::atoi(v);
   cluster_inv_ = half_fwd_ && !getenv_flag("HHE_NO_CLUSTER");
   dev_.strict_cluster = getenv_flag("HHE_STRICT_CLUSTER");
+#ifdef HHE_CUDA
+  dev_.pdl = !getenv_flag("HHE_NO_PDL");
+#endif
   dev_.ordinal = device;
   // L2 prefetch (cp.async.bulk.prefetch.L2 by one thread per CTA pair) of the operands of the pair that starts one full wave
   // later. Measured on B200 (profiles/r2_ab_prefetch.txt): the plain transforms gain 3-8 % (their load phase is a chain of DRAM

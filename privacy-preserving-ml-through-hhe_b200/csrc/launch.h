@@ -37,9 +37,19 @@ struct BodyBounds<B, decltype(void(B::kMinBlocks))> {
   static constexpr int kT = B::kMaxThreads, kM = B::kMinBlocks;
 };
 
+// Programmatic dependent launch (PDL): every kernel is launched with the programmatic-stream-serialization attribute and starts with
+// griddepcontrol.wait (all memory of the preceding kernel is visible after it; a no-op for an ordinary launch) followed by
+// griddepcontrol.launch_dependents, so the NEXT kernel's launch and CTA set-up overlap this kernel's last wave instead of
+// starting after it has drained. The engine's chains are hundreds of short dependent kernels (518 rotations x 3 per PASTA block).
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 template <class Body>
 __global__ void __launch_bounds__(BodyBounds<Body>::kT, BodyBounds<Body>::kM) kernel_entry(const Body body) {
   extern __shared__ __align__(16) unsigned char hhe_smem[];
+  pdl_prologue();
   body(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
 }
 
@@ -70,6 +80,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BodyBounds<Body>::kT
   extern __shared__ __align__(16) unsigned char hhe_smem[];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
+  pdl_prologue();
   body.phase1(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
   if (BodyPeerSmem<Body>::value || strict)
     cluster.sync();
@@ -90,6 +101,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(BodyBounds<Body>::kT
   extern __shared__ __align__(16) unsigned char hhe_smem[];
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
+  pdl_prologue();
   body.phase1(static_cast<int>(blockIdx.x), static_cast<int>(blockDim.x), hhe_smem);
   cluster.sync();
   unsigned char *peers[8];
@@ -292,6 +304,24 @@ struct Device {
 #endif
   }
 
+#ifdef HHE_CUDA
+  bool pdl = true;  // programmatic dependent launch (HHE_NO_PDL=1 switches it off)
+  template <class Kernel, class... Args>
+  void launch_ex(Kernel kernel, size_t grid, int nt, size_t smem_bytes, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(nt));
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cuda_check(cudaLaunchKernelEx(&cfg, kernel, args...), "cudaLaunchKernelEx");
+  }
+#endif
+
   template <class Body>
   void launch(const Body &body, size_t grid, int nt, size_t smem_bytes) {
     if (grid == 0) return;
@@ -318,7 +348,7 @@ struct Device {
         conf = smem_bytes;
       }
     }
-    kernel_entry<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
+    launch_ex(kernel_entry<Body>, grid, nt, smem_bytes, body);
     cuda_check(cudaGetLastError(), "kernel launch");
     if (profiling) {
       cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
@@ -359,7 +389,7 @@ struct Device {
         conf = smem_bytes;
       }
     }
-    kernel_entry_c8<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body);
+    launch_ex(kernel_entry_c8<Body>, grid, nt, smem_bytes, body);
     cuda_check(cudaGetLastError(), "cluster-8 kernel launch");
     if (profiling) {
       cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
@@ -405,7 +435,7 @@ struct Device {
         conf = smem_bytes;
       }
     }
-    kernel_entry_c2<Body><<<static_cast<unsigned>(grid), nt, smem_bytes, stream>>>(body, strict_cluster ? 1 : 0);
+    launch_ex(kernel_entry_c2<Body>, grid, nt, smem_bytes, body, strict_cluster ? 1 : 0);
     cuda_check(cudaGetLastError(), "cluster kernel launch");
     if (profiling) {
       cuda_check(cudaEventRecord(ev_b, stream), "cudaEventRecord");
