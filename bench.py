@@ -574,6 +574,7 @@ def main():
             fc["reference_1core_s_per_sample"] = per_sample
             fc["reference_kind"] = "composed from the reference's per-operation times measured in this run (block + multiply + relinearize + 355 key switches)"
             fc["speedup_vs_1core"] = fc["value"] * per_sample
+            configs["config3_ecg_batch"] = "see the top-level `fc` object (the same measurement, sharded over the ranks at N > 1)"
         ctx.close()
         fac = lambda n_: R.Ref(n_, common.T, None, seed=5, steps=(0, -1), default_gk=False)  # noqa: E731
         configs["config5_primitive_sweep"] = BC.config5(stream, peak, fac)

@@ -63,9 +63,11 @@ class Engine {
   void multiply_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, const u32 *nolift = nullptr);
   void galois(const u64 *a, u32 elt, u64 *out, size_t items);
   // out[c] = ModDown(sum_J NTT(target_J) * key) + base_c ; target/base given with item strides (words)
+  // accum (optional, [items][2][L][N], may alias out): out = accum + result
   void key_switch(const u64 *target, size_t tstride, const W2 *key, const u64 *base0, const u64 *base1, size_t bstride,
-                  u64 *out, size_t items);
-  void apply_galois(const u64 *a, u32 elt, const W2 *key, u64 *out, size_t items);
+                  u64 *out, size_t items, const u64 *accum = nullptr);
+  void apply_galois(const u64 *a, u32 elt, const W2 *key, u64 *out, size_t items, const u64 *accum = nullptr);
+  void rotate_rows_add(const u64 *a, int steps, int keyset, u64 *acc, size_t items);  // acc += rotate_rows(a, steps)
   void rotate_rows(const u64 *a, int steps, int keyset, u64 *out, size_t items);
   void rotate_columns(const u64 *a, int keyset, u64 *out, size_t items);
   void relinearize(const u64 *a3, u64 *out, size_t items);

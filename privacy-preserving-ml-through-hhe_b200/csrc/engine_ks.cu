@@ -10,7 +10,15 @@ void Engine::galois(const u64 *a, u32 elt, u64 *out, size_t items) {
 }
 
 void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const u64 *base0, const u64 *base1,
-                        size_t bstride, u64 *out, size_t items) {
+                        size_t bstride, u64 *out, size_t items, const u64 *accum) {
+  if (accum && !(compact_keys_ && !split_ && cluster_inv_)) {
+    // only the FP64 cluster path folds the accumulation into its store: elsewhere key switch first, then add
+    Scope tmp_scope(*this);
+    u64 *tmp = scratch(items * ct_words());
+    key_switch(target, tstride, key, base0, base1, bstride, tmp, items, nullptr);
+    add(accum, tmp, out, items);
+    return;
+  }
   Scope sc(*this);
   const int K = P_.K;
   u64 *acc = scratch(items * 2 * K * P_.N);
@@ -33,7 +41,7 @@ void Engine::key_switch(const u64 *target, size_t tstride, const W2 *key, const 
     if (cluster_inv_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
         using Body = InvClusterBody<LOGV, PlanModDownAdd>;
-        Body body{PlanModDownAdd{acc, base0, base1, bstride, out}, dC_, twref(), pf_limbs_, static_cast<int>(items * 2 * P_.L)};
+        Body body{PlanModDownAdd{acc, base0, base1, bstride, out, accum}, dC_, twref(), pf_limbs_, static_cast<int>(items * 2 * P_.L)};
         dev_.launch_cluster2(body, items * 2 * P_.L * 2, half_threads(LOGV), ntt_smem_words(1 << LOGV) * 8);
       });
       return;
@@ -89,11 +97,26 @@ void Engine::launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, 
   });
 }
 
-void Engine::apply_galois(const u64 *a, u32 elt, const W2 *key, u64 *out, size_t items) {
+void Engine::apply_galois(const u64 *a, u32 elt, const W2 *key, u64 *out, size_t items, const u64 *accum) {
   Scope sc(*this);
   u64 *g = scratch(items * ct_words());
   galois(a, elt, g, items);
-  key_switch(g + static_cast<size_t>(P_.L) * P_.N, ct_words(), key, g, nullptr, ct_words(), out, items);
+  key_switch(g + static_cast<size_t>(P_.L) * P_.N, ct_words(), key, g, nullptr, ct_words(), out, items, accum);
+}
+
+// acc += rotate_rows(a, steps): with the step's own key the addition is folded into the key switch's last store (no separate
+// 6 MiB element-wise pass); a NAF chain rotates first and adds afterwards
+void Engine::rotate_rows_add(const u64 *a, int steps, int keyset, u64 *acc, size_t items) {
+  const u32 elt = steps ? P_.galois_elt_from_step(steps) : 0;
+  const W2 *key = elt ? find_key(keyset, elt) : nullptr;
+  if (key) {
+    apply_galois(a, elt, key, acc, items, acc);
+    return;
+  }
+  Scope sc(*this);
+  u64 *tmp = scratch(items * ct_words());
+  rotate_rows(a, steps, keyset, tmp, items);
+  add(acc, tmp, acc, items);
 }
 
 void Engine::rotate_rows(const u64 *a, int steps, int keyset, u64 *out, size_t items) {

@@ -106,7 +106,7 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
       // corr_mac and intt_moddown in one launch (RotTailBody): they are independent and overlap
       HHE_DISPATCH_LOG(P_.logn - 1, {
         RotTailBody<LOGV> body{
-            Corr0MacHalfBody<LOGV>{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), 2, c1n},
+            Corr0MacHalfBody<LOGV>{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), 2, c1n, dw, dw},
             InvClusterBody<LOGV, PlanModDownGalois>{PlanModDownGalois{acc, nullptr, g1, e1, P_.logn}, dC_, twref(), pf_limbs_, static_cast<int>(nb * L)},
             static_cast<int>(nb * L * 4)};
         dev_.launch_cluster2(body, nb * L * 6, half_threads(LOGV), half_smem(LOGV));
@@ -128,7 +128,7 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     }
     if (half_fwd_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
-        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), pair ? 2 : 1, c1n};
+        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), pair ? 2 : 1, c1n, dw, dw};
         dev_.launch(body, nb * L * (pair ? 4 : 2), half_threads(LOGV), half_smem(LOGV));
       });
     } else {
@@ -154,11 +154,46 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_
     rotate_rows(state, kPastaT, 0, tmp, nb);
     add(state, tmp, state, nb);
   }
-  dev_.d2d(rot, state, nb * ctw * 8);
-  for (int j = 1; j < N1; ++j) rotate_rows(rot + (j - 1) * nb * ctw, -1, 0, rot + j * nb * ctw, nb);
   const TabMap mq = map_mod(2 * P_.L, P_.L, 0);
-  // every baby rotation is multiplied with 8 diagonals: transform each once (in place), then the products are element-wise
-  ntt(rot, rot, nb * N1, 2 * P_.L, mq, false);
+  if (compact_keys_ && half_fwd_ && cluster_inv_ && !getenv_flag("HHE_NO_RESIDENT") && !getenv_flag("HHE_NO_BSGS_RESIDENT")) {
+    // The 15 chained baby rotations on the NTT-resident chain (as the diagonal layer's, without the plaintext product): every baby
+    // rotation is wanted in NTT form anyway (it is multiplied with 8 diagonals element-wise), so rot[j] is written directly as
+    // (c0n, c1n) by rot_tail; per rotation 64 + 2 + 8 + 16 limb transforms instead of 72 + 18 for the generic rotation plus 16 for
+    // the forward transform afterwards. Bit-identical (same identities as affine_diagonal_resident).
+    const int L = P_.L, K = P_.K;
+    const u32 e1 = P_.galois_elt_from_step(-1);
+    const W2 *k1 = need_key(0, e1);
+    const u32 *perm = ntt_perm(e1);
+    u64 *g1 = scratch(nb * dw), *acc = scratch(nb * 2 * K * N);
+    TabMap msp2{};
+    msp2.id[0] = msp2.id[1] = static_cast<unsigned char>(K - 1);
+    ntt(state, rot, nb, 2 * L, mq, false);  // rot[0] = NTT(state)
+    {  // digits of the first key switch: galois(c1) in coefficient form, items strided by a whole ciphertext
+      Scope inner_sc(*this);
+      u64 *c1c = scratch(nb * dw);
+      strided_copy(state + dw, ctw, c1c, dw, dw, nb);
+      GaloisBody gb{c1c, g1, dC_, inv_mod_2n(e1, 2 * N), nb * dw};
+      dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
+    }
+    for (int j = 1; j < N1; ++j) {
+      u64 *prev = rot + static_cast<size_t>(j - 1) * nb * ctw, *cur = rot + static_cast<size_t>(j) * nb * ctw;
+      launch_ks_digits(g1, dw, k1, acc, nb, prev + dw, ctw, perm);
+      ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, 2, msp2, true, static_cast<size_t>(2) * K * N,
+          static_cast<size_t>(K) * N);
+      HHE_DISPATCH_LOG(P_.logn - 1, {
+        RotTailBody<LOGV> body{
+            Corr0MacHalfBody<LOGV>{acc, prev, cur, perm, nullptr, nullptr, dC_, twref(), 0, nullptr, 0, static_cast<int>(nb * L), 2, cur + dw, ctw, ctw},
+            InvClusterBody<LOGV, PlanModDownGalois>{PlanModDownGalois{acc, nullptr, g1, e1, P_.logn}, dC_, twref(), 0, static_cast<int>(nb * L)},
+            static_cast<int>(nb * L * 4)};
+        dev_.launch_cluster2(body, nb * L * 6, half_threads(LOGV), half_smem(LOGV));
+      });
+    }
+  } else {
+    dev_.d2d(rot, state, nb * ctw * 8);
+    for (int j = 1; j < N1; ++j) rotate_rows(rot + (j - 1) * nb * ctw, -1, 0, rot + j * nb * ctw, nb);
+    // every baby rotation is multiplied with 8 diagonals: transform each once (in place), then the products are element-wise
+    ntt(rot, rot, nb * N1, 2 * P_.L, mq, false);
+  }
   for (int k = 0; k < N2; ++k) {
     // the 16 diagonals of this giant step are encoded, lifted and transformed as one batch ([j][nd] items), then one pass over
     // the baby rotations forms the inner sum: every residue of `inner` is written once
@@ -170,8 +205,7 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_
       ntt(inner, outer, nb, 2 * P_.L, mq, true);
     } else {
       ntt(inner, inner, nb, 2 * P_.L, mq, true);
-      rotate_rows(inner, -k * N1, 0, tmp, nb);
-      add(outer, tmp, outer, nb);
+      rotate_rows_add(inner, -k * N1, 0, outer, nb);
     }
   }
   dev_.d2d(state, outer, nb * ctw * 8);
@@ -301,13 +335,10 @@ void Engine::mask(const u64 *a, const u64 *d_mask_slots, u32 n, u64 *out, size_t
 void Engine::flatten(const u64 *in, size_t per, int keyset, u64 *out, size_t items) {
   Scope sc(*this);
   const size_t ctw = ct_words();
-  u64 *gath = scratch(items * ctw), *rot = scratch(items * ctw);
+  u64 *gath = scratch(items * ctw);
   for (size_t i = 0; i < per; ++i) {
     strided_copy(in + i * ctw, per * ctw, i ? gath : out, ctw, ctw, items);  // block i of every group in one gather launch
-    if (i) {
-      rotate_rows(gath, -static_cast<int>(i * kPastaT), keyset, rot, items);
-      add(out, rot, out, items);
-    }
+    if (i) rotate_rows_add(gath, -static_cast<int>(i * kPastaT), keyset, out, items);
   }
 }
 
@@ -350,19 +381,27 @@ void Engine::vec_sum(const u64 *a, size_t n, int keyset, u64 *out, size_t items)
     src0 = acopy;
   }
   std::vector<int> path;
-  for (auto &s : seqs) {
+  for (size_t si = 0; si < seqs.size(); ++si) {
+    const auto &s = seqs[si];
     size_t common = 0;
     while (common < path.size() && common < s.size() && path[common] == s[common]) ++common;
     path.resize(common);
+    // a sequence that no later one extends is a leaf: its last key switch adds straight into the running sum (the addition is folded
+    // into the key switch's store); a sequence that is also the prefix of the next one keeps its result for it
+    const bool leaf = !s.empty() && !(si + 1 < seqs.size() && seqs[si + 1].size() > s.size() &&
+                                      std::equal(s.begin(), s.end(), seqs[si + 1].begin()));
     for (size_t d = common; d < s.size(); ++d) {
       const u32 e = P_.galois_elt_from_step(s[d]);
-      apply_galois(d == 0 ? src0 : level[d], e, need_key(keyset, e), level[d + 1], items);
+      const bool fold = leaf && d + 1 == s.size();
+      apply_galois(d == 0 ? src0 : level[d], e, need_key(keyset, e), fold ? acc : level[d + 1], items, fold ? acc : nullptr);
       path.push_back(s[d]);
     }
     if (s.empty())
       add(acc, src0, acc, items);
-    else
+    else if (!leaf)
       add(acc, level[s.size()], acc, items);
+    else
+      path.pop_back();  // the leaf's last level was never materialised
   }
 }
 

@@ -1897,6 +1897,8 @@ struct Corr0MacHalfBody {
   int pf, nl;         // L2 prefetch distance in limbs (0: off), total limbs of the launch
   int comps;          // 1: component 0 only; 2: both
   u64 *c1_out;        // [items][L][N] NTT form of the new component 1 (comps == 2)
+  size_t cin_stride, cout_stride;  // words between items in c0_in and in c0_out / c1_out (L*N when they are dense per component)
+  // D == nullptr: no plaintext product (the baby rotations of the BSGS layer only want the rotated ciphertext in NTT form)
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
     constexpr int S = 1 << LOGH;
@@ -1908,9 +1910,9 @@ struct Corr0MacHalfBody {
       const size_t itf = lf / L;
       if (fi == 0) cta_prefetch_l2(acc + ((itf * 2) * K + (K - 1)) * N, sizeof(u64) * N);
       cta_prefetch_l2(acc + ((itf * 2) * K + fi) * N, sizeof(u64) * N);
-      cta_prefetch_l2(c0_in + (itf * L + fi) * N, sizeof(u64) * N);
-      if (dstride) cta_prefetch_l2(D + (didx ? didx[itf] : itf) * dstride + static_cast<size_t>(fi) * N, sizeof(u64) * N);
-      cta_prefetch_l2(sum + (itf * 2 * L + fi) * N, sizeof(u64) * N);
+      cta_prefetch_l2(c0_in + itf * cin_stride + static_cast<size_t>(fi) * N, sizeof(u64) * N);
+      if (D && dstride) cta_prefetch_l2(D + (didx ? didx[itf] : itf) * dstride + static_cast<size_t>(fi) * N, sizeof(u64) * N);
+      if (D) cta_prefetch_l2(sum + (itf * 2 * L + fi) * N, sizeof(u64) * N);
     }
     const DevMod mi = C->mod[i], msp = C->mod[K - 1];
     const u64 *sp = acc + ((item * 2 + c) * K + (K - 1)) * N;
@@ -1918,10 +1920,11 @@ struct Corr0MacHalfBody {
     const double qd = C->qf[i], qi = C->qinvf[i];
     const F64Tw twk = tw.fwd_f(i);
     const u64 *a0 = acc + ((item * 2 + c) * K + i) * N + hoff;
-    const u64 *cin = c0_in + (item * L + i) * N;
-    u64 *cout = (c ? c1_out : c0_out) + (item * L + i) * N + hoff;
-    const u64 *d = D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + hoff;
-    u64 *s0 = sum + ((item * 2 + c) * L + i) * N + hoff;
+    const u64 *cin = c0_in + item * cin_stride + static_cast<size_t>(i) * N;
+    u64 *cout = (c ? c1_out : c0_out) + item * cout_stride + static_cast<size_t>(i) * N + hoff;
+    const bool mac = D != nullptr;
+    const u64 *d = mac ? D + (didx ? didx[item] : item) * dstride + static_cast<size_t>(i) * N + hoff : nullptr;
+    u64 *s0 = mac ? sum + ((item * 2 + c) * L + i) * N + hoff : nullptr;
     fwd_half_transform_f64<LOGH, RawCorr, SmemIO, kF64AnyOut16, 512, false>(fm, twk, qd, qi, h, nt,
                                                                             RawCorr{sp, C->half_sp, C->half_sp_mod_q[i], mi.q, mi, msp});
     const u32 *pm = perm + hoff;
@@ -1940,8 +1943,8 @@ struct Corr0MacHalfBody {
           const int j = j0 + u * nt < S ? j0 + u * nt : j0;
           cv[u] = c ? 0 : cin[pj[u]];
           av[u] = a0[j];
-          dv[u] = d[j];
-          sv[u] = s0[j];
+          dv[u] = mac ? d[j] : 0;
+          sv[u] = mac ? s0[j] : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -1951,7 +1954,7 @@ struct Corr0MacHalfBody {
             const double k0 = f_mulmod_const(f_add(u_to_f(av[u]), -fm[pidx(j)]), isp, qd);
             const u64 cc = f_canonical(f_add(u_to_f(cv[u]), k0), qd, qi);
             cout[j] = cc;
-            s0[j] = f_canonical(f_add(f_mulmod_var(u_to_f(cc), u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
+            if (mac) s0[j] = f_canonical(f_add(f_mulmod_var(u_to_f(cc), u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
           }
         }
       }
@@ -2030,12 +2033,13 @@ struct StoreModDownAdd {
   u64 *out;
   D2 ninv, isp;
   double q, qinv, qsp, half_sp, half_i;
+  const u64 *add2;  // optional second addend with out's indexing (a running sum the result is accumulated into; may alias out)
   HD double load(int) const { return 0.0; }
   HD void group_out(int, const double *) const {}
   struct Aux {
-    u64 s, b;
+    u64 s, b, a2;
   };
-  HD Aux aux(int j) const { return Aux{sp[j], base ? base[j] : 0}; }
+  HD Aux aux(int j) const { return Aux{sp[j], base ? base[j] : 0, add2 ? add2[j] : 0}; }
   HD void store(int j, double v) const { store(j, v, aux(j)); }
   HD void store(int j, double v, const Aux &ax) const {
     const double x = f_mulmod_const(v, ninv, q);
@@ -2044,6 +2048,7 @@ struct StoreModDownAdd {
     const double y = f_add(f_add(x, -t), half_i);  // |y| < 5q
     double c = f_mulmod_const(y, isp, q);          // |c| <= 1.5q
     if (base) c = f_add(c, u_to_f(ax.b));
+    if (add2) c = f_add(c, u_to_f(ax.a2));         // <= 3.5q
     out[j] = f_canonical(c, q, qinv);
   }
 };
@@ -2073,7 +2078,7 @@ struct InttModDownAddBody {
     SYNC();
     const StoreModDownAdd st{sp, bs ? bs + item * bstride + static_cast<size_t>(i) * S : nullptr, out + ((item * 2 + c) * L + i) * S,
                              C->n_inv_f[i], C->inv_sp_f[i], qd, qi, C->qf[K - 1], static_cast<double>(C->half_sp),
-                             static_cast<double>(C->half_sp_mod_q[i])};
+                             static_cast<double>(C->half_sp_mod_q[i]), nullptr};
     ntt_inv_core_f64<LOGS, 0, StoreModDownAdd, whole_threads(LOGS)>(fm, tw.inv_f(i), qd, qi, 0, nt, st);
   }
 };
@@ -2231,6 +2236,7 @@ struct PlanModDownAdd {  // InttModDownAddBody
   const u64 *acc, *base0, *base1;
   size_t bstride;
   u64 *out;
+  const u64 *accum;  // optional [items][2][L][N]: out = accum + key-switch result (+ base); may alias out
   HD int tab(int lb, const DevConsts *C) const { return lb % C->L; }
   HD const u64 *src(int lb, const DevConsts *C, int N) const {
     const int L = C->L;
@@ -2249,7 +2255,8 @@ struct PlanModDownAdd {  // InttModDownAddBody
     const u64 *bs = c ? base1 : base0;
     return StoreModDownAdd{acc + ((item * 2 + c) * K + (K - 1)) * N, bs ? bs + item * bstride + static_cast<size_t>(i) * N : nullptr,
                            out + ((item * 2 + c) * L + i) * N, C->n_inv_f[i], C->inv_sp_f[i], C->qf[i], C->qinvf[i], C->qf[K - 1],
-                           static_cast<double>(C->half_sp), static_cast<double>(C->half_sp_mod_q[i])};
+                           static_cast<double>(C->half_sp), static_cast<double>(C->half_sp_mod_q[i]),
+                           accum ? accum + ((item * 2 + c) * L + i) * N : nullptr};
   }
 };
 
