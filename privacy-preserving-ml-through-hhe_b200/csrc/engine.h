@@ -100,7 +100,8 @@ class Engine {
                    const u32 *didx, u64 nonce, bool use_bsgs, u64 *d_out);
   void affine_diagonal(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
   void affine_diagonal_resident(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
-  const u32 *ntt_perm(u32 elt);
+  const u32 *ntt_perm(u32 elt);                                      // NTT-slot permutation of a Galois element (gather form)
+  const u32 *ntt_perm_inv(u32 elt) { return ntt_perm(elt) + P_.N; }  // its inverse (scatter form)
   void affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_t nd, const u32 *didx);
   void feistel(u64 *state, size_t nb);
   const W2 *need_key(int kind, u32 elt) const;
@@ -120,6 +121,8 @@ class Engine {
   bool cluster_inv_ = false;  // FP64 inverse transforms as two-CTA clusters (half-limb CTAs, last stage over distributed shared memory)
   int pf_ntt_ = 0, pf_limbs_ = 0, pf_items_ = 0;  // L2 prefetch distances (limbs: plain transforms / other half-limb kernels; items: ks_digits); 0 = off
   bool half_fwd_ = false;  // FP64 forward transforms of lift_ntt / ntt_mac / corr0_mac as half-limb CTAs (two per SM)
+  // reuse / perm: the NTT form of the source polynomial and the slot permutation of the Galois element (digit J on key limb J
+  // needs no transform); perm == nullptr with reuse != nullptr: `reuse` is already stored permuted (read linearly)
   void launch_ks_digits(const u64 *target, size_t tstride, const W2 *key, u64 *acc, size_t items, const u64 *reuse, size_t reuse_stride,
                         const u32 *perm);  // every key limb is on the FP64 path: keys are stored as doubles (8 bytes per residue)
   DevConsts *dC_ = nullptr;

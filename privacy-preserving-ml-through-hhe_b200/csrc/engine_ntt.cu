@@ -184,8 +184,14 @@ const u32 *Engine::ntt_perm(u32 elt) {
     const u64 e = ((2 * brev(i) + 1) * elt) % m;
     table[i] = static_cast<u32>(brev((e - 1) >> 1));
   }
-  u32 *d = static_cast<u32 *>(dev_.dmalloc(N * sizeof(u32)));
-  dev_.h2d(d, table.data(), N * sizeof(u32));
+  // [0, N): the permutation (gather form); [N, 2N): its inverse (scatter form, ntt_perm_inv)
+  std::vector<u32> both(2 * N);
+  for (u64 i = 0; i < N; ++i) {
+    both[i] = table[i];
+    both[N + table[i]] = static_cast<u32>(i);
+  }
+  u32 *d = static_cast<u32 *>(dev_.dmalloc(2 * N * sizeof(u32)));
+  dev_.h2d(d, both.data(), 2 * N * sizeof(u32));
   dev_.sync();
   perms_[elt] = d;
   return d;

@@ -77,8 +77,21 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
   encode_material(mat, nullptr, kDiag, layer, 0, pt, nd, G);
   lift_ntt(pt, Dg, nd * G);
   ntt_mac(state, D, ds, sum, nb, true, 2, 0, stn, didx);
-  strided_copy(stn, ctw, c0a, dw, dw, nb);
-  strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
+  // half-limb FP64 kernels: both components of the rotated ciphertext stay NTT-resident (Corr0MacHalfBody, comps = 2), the
+  // coefficient form of c1 is never stored (only its Galois image g1, the next key switch's digits), and the two NTT-resident
+  // arrays are kept in the order their next reader wants (permuted by the rotation's slot permutation: corr_mac scatters its outputs
+  // through the inverse permutation, so neither it nor ks_digits has a dependent gather on its critical path)
+  const bool pair = half_fwd_ && cluster_inv_ && !getenv_flag("HHE_NO_CORR_PAIR");
+  const bool fuse_tail = !getenv_flag("HHE_NO_ROT_TAIL");
+  const bool scatter = pair && fuse_tail && !getenv_flag("HHE_NO_SCATTER");
+  if (scatter) {
+    PermCopyBody p0{stn, c0a, perm, ctw, dw, dC_, L, nb * dw}, p1{stn + dw, c1n, perm, ctw, dw, dC_, L, nb * dw};
+    dev_.launch(p0, ew_grid(nb * dw), kEwThreads, 0);
+    dev_.launch(p1, ew_grid(nb * dw), kEwThreads, 0);
+  } else {
+    strided_copy(stn, ctw, c0a, dw, dw, nb);
+    strided_copy(stn + dw, ctw, c1n, dw, dw, nb);
+  }
   strided_copy(state + dw, ctw, c1c, dw, dw, nb);
   u64 *c0_in = c0a, *c0_out = c0b;
   TabMap msp2{};
@@ -87,12 +100,9 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     GaloisBody gb{c1c, g1, dC_, e1_inv, nb * dw};
     dev_.launch(gb, ew_grid(nb * dw), kEwThreads, 0);
   }
-  // half-limb FP64 kernels: both components of the rotated ciphertext stay NTT-resident (Corr0MacHalfBody, comps = 2), the
-  // coefficient form of c1 is never stored (only its Galois image g1, the next key switch's digits)
-  const bool pair = half_fwd_ && cluster_inv_ && !getenv_flag("HHE_NO_CORR_PAIR");
-  const bool fuse_tail = !getenv_flag("HHE_NO_ROT_TAIL");
+  const u32 *pinv = scatter ? ntt_perm_inv(e1) : nullptr;
   for (int i = 1; i < kPastaT; ++i) {
-    launch_ks_digits(g1, dw, k1, acc, nb, c1n, dw, perm);
+    launch_ks_digits(g1, dw, k1, acc, nb, c1n, dw, scatter ? nullptr : perm);
     // inverse NTT of the two special limbs acc[0][K-1], acc[1][K-1] (K*N words apart inside an item), then of acc[1][i<L]
     // with the ModDown and the next rotation's Galois map fused into the store
     ntt(acc + static_cast<size_t>(K - 1) * N, acc + static_cast<size_t>(K - 1) * N, nb, 2, msp2, true, static_cast<size_t>(2) * K * N,
@@ -106,7 +116,8 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
       // corr_mac and intt_moddown in one launch (RotTailBody): they are independent and overlap
       HHE_DISPATCH_LOG(P_.logn - 1, {
         RotTailBody<LOGV> body{
-            Corr0MacHalfBody<LOGV>{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), 2, c1n, dw, dw},
+            Corr0MacHalfBody<LOGV>{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), 2, c1n, dw, dw,
+                                   pinv},
             InvClusterBody<LOGV, PlanModDownGalois>{PlanModDownGalois{acc, nullptr, g1, e1, P_.logn}, dC_, twref(), pf_limbs_, static_cast<int>(nb * L)},
             static_cast<int>(nb * L * 4)};
         dev_.launch_cluster2(body, nb * L * 6, half_threads(LOGV), half_smem(LOGV));
@@ -128,7 +139,8 @@ void Engine::affine_diagonal_resident(u64 *state, const u32 *mat, int layer, siz
     }
     if (half_fwd_) {
       HHE_DISPATCH_LOG(P_.logn - 1, {
-        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), pair ? 2 : 1, c1n, dw, dw};
+        Corr0MacHalfBody<LOGV> body{acc, c0_in, c0_out, perm, D, sum, dC_, twref(), ds, didx, pf_limbs_, static_cast<int>(nb * L), pair ? 2 : 1, c1n, dw, dw,
+                                    nullptr};
         dev_.launch(body, nb * L * (pair ? 4 : 2), half_threads(LOGV), half_smem(LOGV));
       });
     } else {
@@ -182,7 +194,8 @@ void Engine::affine_bsgs(u64 *state, const u32 *mat, int layer, size_t nb, size_
           static_cast<size_t>(K) * N);
       HHE_DISPATCH_LOG(P_.logn - 1, {
         RotTailBody<LOGV> body{
-            Corr0MacHalfBody<LOGV>{acc, prev, cur, perm, nullptr, nullptr, dC_, twref(), 0, nullptr, 0, static_cast<int>(nb * L), 2, cur + dw, ctw, ctw},
+            Corr0MacHalfBody<LOGV>{acc, prev, cur, perm, nullptr, nullptr, dC_, twref(), 0, nullptr, 0, static_cast<int>(nb * L), 2, cur + dw, ctw, ctw,
+                                   nullptr},  // natural order: the baby rotations are multiplied element-wise afterwards
             InvClusterBody<LOGV, PlanModDownGalois>{PlanModDownGalois{acc, nullptr, g1, e1, P_.logn}, dC_, twref(), 0, static_cast<int>(nb * L)},
             static_cast<int>(nb * L * 4)};
         dev_.launch_cluster2(body, nb * L * 6, half_threads(LOGV), half_smem(LOGV));

@@ -713,14 +713,15 @@ struct KsDigitsTmemBody {
       if (reuse && J == k) {
         // NTT_J(target_J) is the permuted NTT of the source polynomial: no transform, straight to the accumulation
         const u64 *rn = reuse + static_cast<size_t>(b) * reuse_stride + static_cast<size_t>(J) * N;
-        const u32 *pm = perm + static_cast<size_t>(h) * S;
+        const u32 *pm = perm ? perm + static_cast<size_t>(h) * S : nullptr;
         FOR_THREADS(tid, nt) {
           const KsMacOut mac{k0, k1, G, nt, q, qi, TmemAcc::make(tbase, tid, nt, gpt * 2, emu)};
           for (int g = tid; g < G; g += nt) {
             u32 pj[8];
             double x[8];
+            // perm == nullptr: the producer stored the transform already permuted (corr_mac's scatter store): 8 consecutive words
 #pragma unroll
-            for (int e = 0; e < 8; ++e) pj[e] = pm[8 * g + e];
+            for (int e = 0; e < 8; ++e) pj[e] = pm ? pm[8 * g + e] : static_cast<u32>(h * S + 8 * g + e);
 #pragma unroll
             for (int e = 0; e < 8; ++e) x[e] = u_to_f(rn[pj[e]]);
             mac.group_out(g, x);
@@ -834,9 +835,9 @@ struct KsDigitsSplitBody {
     }
     if (reuse && J == k) {  // NTT_J(target_J) is the permuted NTT of the source polynomial
       const u64 *rn = reuse + static_cast<size_t>(b) * reuse_stride + static_cast<size_t>(J) * N;
-      const u32 *pm = perm + static_cast<size_t>(h) * S;
+      const u32 *pm = perm ? perm + static_cast<size_t>(h) * S : nullptr;
       FOR_THREADS(tid, nt) {
-        for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(rn[pm[i]]);
+        for (int i = tid; i < S; i += nt) fm[pidx(i)] = u_to_f(rn[pm ? pm[i] : static_cast<u32>(h * S + i)]);
       }
       SYNC();
     } else {
@@ -1689,6 +1690,29 @@ struct StridedCopyBody {
   }
 };
 
+// dst[r][l][j] = src[r][l][perm[j]]: a limb-wise slot permutation while copying (start of the resident chain: the transforms of the
+// state are stored the way the first rotation will read them)
+struct PermCopyBody {
+  static constexpr const char *kName = "perm_copy";
+  const u64 *src;
+  u64 *dst;
+  const u32 *perm;
+  size_t sstride, dstride;  // words between rows
+  const DevConsts *C;
+  int limbs;
+  size_t total;  // rows * limbs * N
+  HD void operator()(int bid, int nt, unsigned char *) const {
+    const size_t N = C->N;
+    FOR_THREADS(tid, nt) {
+      const size_t g = static_cast<size_t>(bid) * nt + tid;
+      if (g < total) {
+        const size_t j = g & (N - 1), limb = g >> C->logn, r = limb / limbs, l = limb % limbs;
+        dst[r * dstride + l * N + j] = src[r * sstride + l * N + perm[j]];
+      }
+    }
+  }
+};
+
 // ModDown of component 1 only: c1[i][j] = (acc1[i][j] - (r1[j] mod q_i) + half_i) * q_sp^-1, acc1 in coefficient form
 struct ModDownC1Body {
   static constexpr const char *kName = "moddown_c1";
@@ -1898,6 +1922,10 @@ struct Corr0MacHalfBody {
   int comps;          // 1: component 0 only; 2: both
   u64 *c1_out;        // [items][L][N] NTT form of the new component 1 (comps == 2)
   size_t cin_stride, cout_stride;  // words between items in c0_in and in c0_out / c1_out (L*N when they are dense per component)
+  // pinv != nullptr: c0_in is stored ALREADY PERMUTED (read linearly) and both outputs are stored permuted for their next reader
+  // (scatter through the inverse permutation): the dependent index -> gather pair of loads leaves the epilogue's critical path, and
+  // ks_digits reads its reused digit as consecutive words. A store does not stall anybody; a gather stalls its warp for two round trips.
+  const u32 *pinv;
   // D == nullptr: no plaintext product (the baby rotations of the BSGS layer only want the rotated ciphertext in NTT form)
   HD void operator()(int bid, int, unsigned char *smem) const {
     constexpr int nt = half_threads(LOGH);
@@ -1934,14 +1962,17 @@ struct Corr0MacHalfBody {
       for (int j0 = tid; j0 < S; j0 += nt * U) {
         u32 pj[U];
         u64 cv[U], av[U], dv[U], sv[U];
-        if (!c) {
+        if (pinv) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) pj[u] = pinv[hoff + (j0 + u * nt < S ? j0 + u * nt : j0)];  // where this output is stored
+        } else if (!c) {
 #pragma unroll
           for (int u = 0; u < U; ++u) pj[u] = pm[j0 + u * nt < S ? j0 + u * nt : j0];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + u * nt < S ? j0 + u * nt : j0;
-          cv[u] = c ? 0 : cin[pj[u]];
+          cv[u] = c ? 0 : (pinv ? cin[hoff + j] : cin[pj[u]]);
           av[u] = a0[j];
           dv[u] = mac ? d[j] : 0;
           sv[u] = mac ? s0[j] : 0;
@@ -1953,7 +1984,10 @@ struct Corr0MacHalfBody {
             // k = (acc - NTT(corr)) * q_sp^-1: |acc - NTT(corr)| <= 11q, |k| <= 2.6q
             const double k0 = f_mulmod_const(f_add(u_to_f(av[u]), -fm[pidx(j)]), isp, qd);
             const u64 cc = f_canonical(f_add(u_to_f(cv[u]), k0), qd, qi);
-            cout[j] = cc;
+            if (pinv)
+              (cout - hoff)[pj[u]] = cc;
+            else
+              cout[j] = cc;
             if (mac) s0[j] = f_canonical(f_add(f_mulmod_var(u_to_f(cc), u_to_f(dv[u]), qd, qi), u_to_f(sv[u])), qd, qi);
           }
         }
