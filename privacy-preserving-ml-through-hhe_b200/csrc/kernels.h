@@ -117,7 +117,7 @@ struct RawCorr {  // corr[j] = (r0[j] mod q_i) - (half mod q_i), r0 = acc0[speci
 // With WARP_LOCAL (CTA of NT = S/16 threads, two folded stages) warp w folds the residues i, i + S/2 with
 // i in [256 w, 256 w + 256): exactly the residues its own threads read in the LAST register pass of the previous
 // transform that used the same buffer, so back-to-back transforms need only a warp-level sync in between.
-constexpr bool half_warp_local(int logh, int nt) { return NttSchedule_first(logh) == 1 && nt * 16 == (1 << logh); }
+HD constexpr bool half_warp_local(int logh, int nt) { return NttSchedule_first(logh) == 1 && nt * 16 == (1 << logh); }
 
 template <int LOGH, class LD, bool WARP_LOCAL = false>
 HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int nt, const LD &ld) {
@@ -220,10 +220,10 @@ HD void fwd_half_load_f64(double *fm, F64Tw twk, double q, double qi, int h, int
 }
 
 // CTA size of the whole-limb kernels (Engine: ntt_threads)
-constexpr int whole_threads(int logs) { return (1 << logs) / 8 < 32 ? 32 : ((1 << logs) / 8 > HHE_MAX_THREADS ? HHE_MAX_THREADS : (1 << logs) / 8); }
+HD constexpr int whole_threads(int logs) { return (1 << logs) / 8 < 32 ? 32 : ((1 << logs) / 8 > HHE_MAX_THREADS ? HHE_MAX_THREADS : (1 << logs) / 8); }
 
 // CTA size of the half-limb kernels (one radix-8 group per thread and pass at least, 512 threads at most)
-constexpr int half_threads(int logh, int maxt = 512) { return (1 << logh) / 8 < 32 ? 32 : ((1 << logh) / 8 > maxt ? maxt : (1 << logh) / 8); }
+HD constexpr int half_threads(int logh, int maxt = 512) { return (1 << logh) / 8 < 32 ? 32 : ((1 << logh) / 8 > maxt ? maxt : (1 << logh) / 8); }
 
 // the register passes that follow fwd_half_load_f64; results in shared memory (or handed to IO::group_out), |.| <= MAXOUT16/16 q
 template <int LOGH, class IO = SmemIO, int MAXOUT16 = kF64AnyOut16, int MAXT = 512>
@@ -243,7 +243,7 @@ HD void fwd_half_passes_f64(double *fm, F64Tw twk, double q, double qi, int h, i
 // read back, 14 % of the LSU wavefronts of a key-switch digit) and one barrier less per transform; the FP64 work is unchanged.
 // `before_store`: executed by every thread between its last global load and its first shared-memory store (the key-switch kernel
 // places the barrier there that protects the previous digit's last pass, which is still reading the buffer).
-constexpr bool half_fused_first_pass(int logh, int nt) {
+HD constexpr bool half_fused_first_pass(int logh, int nt) {
 #if defined(HHE_NO_FUSED_FIRST_PASS)
   return false && logh && nt;
 #else
@@ -1132,7 +1132,6 @@ struct AddBody {  // out = a + b
   int limbs;  // limbs per item (size * L)
   size_t total;
   HD void operator()(int bid, int nt, unsigned char *) const {
-    const size_t N = C->N;
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
@@ -1150,7 +1149,6 @@ struct NegateBody {
   const DevConsts *C;
   size_t total;
   HD void operator()(int bid, int nt, unsigned char *) const {
-    const size_t N = C->N;
     FOR_THREADS(tid, nt) {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) out[g] = neg_mod(a[g], C->mod[static_cast<u32>(g >> C->logn) % static_cast<u32>(C->L)].q);
@@ -1635,7 +1633,7 @@ struct BehzScaleRoundBody {
       const size_t g = static_cast<size_t>(bid) * nt + tid;
       if (g < total) {
         const size_t p = g >> C->logn, j = g & (N - 1);
-        u64 z[kMaxLimbs], f[kMaxLimbs];
+        u64 z[kMaxLimbs], f[kMaxLimbs] = {};
         for (int i = 0; i < L; ++i) z[i] = mul_shoup(dq[(p * L + i) * N + j], C->t_ipq[i], C->mod[i].q);
         for (int bb = 0; bb <= L; ++bb) {
           const DevMod mb = C->mod[K + bb];

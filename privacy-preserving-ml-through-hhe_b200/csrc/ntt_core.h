@@ -25,7 +25,7 @@ HD int pidx(int i) { return i + (i >> 4); }
 // that are 8 words apart instead. A bijection on the groups of a warp, so nothing else changes (tools: /tmp-free check
 // in DESIGN.md; ncu: 22% of the shared-memory wavefronts were conflict replays before).
 HD int stride8_group(int g) { return (g & ~0x18) | ((g & 8) << 1) | ((g & 16) >> 1); }
-constexpr size_t ntt_smem_words(int S) { return static_cast<size_t>(S) + (S >> 4); }
+HD constexpr size_t ntt_smem_words(int S) { return static_cast<size_t>(S) + (S >> 4); }
 
 HD void fwd_bfly(u64 &a, u64 &b, W2 w, u64 q, u64 two_q) {
   u64 x = a >= two_q ? a - two_q : a;
@@ -116,7 +116,7 @@ HD void inv_group(u64 *sm, const W2 *__restrict__ tw, u64 q, int logS, int s0, u
 #define HHE_RADIX_LOG 3
 #endif
 constexpr int kRadixLog = HHE_RADIX_LOG;  // stages per register pass (4: radix-16, 3: radix-8)
-constexpr int NttSchedule_first(int logs) { return logs - kRadixLog * ((logs - 1) / kRadixLog); }
+HD constexpr int NttSchedule_first(int logs) { return logs - kRadixLog * ((logs - 1) / kRadixLog); }
 template <int LOGS>
 struct NttSchedule {
   static constexpr int kFirst = LOGS - kRadixLog * ((LOGS - 1) / kRadixLog);  // stages in the odd-sized pass
@@ -195,7 +195,7 @@ struct F64Tw {
   const double *cm;
   int gmin;  // first global stage that has a component-major table (= logN mod 3, or 3 if that is 0)
 };
-constexpr size_t f64tw_offset_c(int g0, int gmin) {
+HD constexpr size_t f64tw_offset_c(int g0, int gmin) {
   size_t off = 0;
   for (int g = gmin; g < g0; g += 3) off += static_cast<size_t>(7) << g;
   return off;
@@ -207,18 +207,18 @@ HD size_t f64tw_offset(int g0, int gmin) {
 }
 
 // bound (units of q/16) of a product whose variable operand is bounded by b16, with one unit of slack
-constexpr int f64_tbound16(int b16) { return 8 + (3 * b16 + 15) / 16 + 1; }
+HD constexpr int f64_tbound16(int b16) { return 8 + (3 * b16 + 15) / 16 + 1; }
 constexpr int kF64Reduced16 = 9;   // q/2 + 1
 constexpr int kF64PassLimit16 = 120;  // a pass may leave at most 7.5q to the next one (a kHalf pass then peaks below 12q)
 constexpr int kF64AnyOut16 = 160;     // what f_canonical / f_reduce callers accept from a transform
 enum F64Mode { kNone = 0, kHalf = 1, kFull = 2 };
 // output bound of a forward pass of R stages entered with bound b16
-constexpr int f64_fwd_out16(int b16, int R, bool half) {
+HD constexpr int f64_fwd_out16(int b16, int R, bool half) {
   for (int s = 0; s < R; ++s) b16 = ((half && s == R - 1) ? kF64Reduced16 : b16) + f64_tbound16(b16);
   return b16;
 }
 // largest intermediate of a kHalf pass: the residues entering its last stage (operands of that stage's products)
-constexpr int f64_fwd_peak16(int b16, int R) {
+HD constexpr int f64_fwd_peak16(int b16, int R) {
   for (int s = 0; s + 1 < R; ++s) b16 += f64_tbound16(b16);
   return b16;
 }
@@ -329,16 +329,16 @@ HD void group_core_f64(double *sm, const double *wv, double q, double qinv, int 
 #pragma unroll
   for (int e = 0; e < E; ++e) x[e] = kGlobalIn ? io.load((hi << (LOGS - S0)) + lo + (e << LG)) : sm[a0 + off(e)];
   group_math_f64<R, INVERSE, MODE>(x, wv, q, qinv);
-  if (kGroupOut) {
+  if constexpr (kGroupOut) {
     io.group_out(g, x);
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int e = 0; e < E; ++e) {
-    if (kGlobalOut)
-      io.store((hi << (LOGS - S0)) + lo + (e << LG), x[e]);
-    else
-      sm[a0 + off(e)] = x[e];
+    for (int e = 0; e < E; ++e) {
+      if (kGlobalOut)
+        io.store((hi << (LOGS - S0)) + lo + (e << LG), x[e]);
+      else
+        sm[a0 + off(e)] = x[e];
+    }
   }
 }
 
