@@ -569,6 +569,7 @@ def main():
                                 "frac_of_hbm_roofline": BYTES_PER_BLOCK[True] * B / bs / 1e9 / peak}
         ctx.set_batch(0)
         configs["config2_mnist_sample"] = BC.config2(ctx, ref, enc_key, sym_key, rngc, peak, ref_ops)
+        configs["next_rows"] = BC.next_rows(ctx, ref, enc_key, sym_key, rngc, ref_ops)
         if fc:
             per_sample = ref_ops["block_s"] + ref_ops["multiply_s"] + ref_ops["relinearize_s"] + BC.KS_COUNT[128] * ref_ops["rotate_s"]
             fc["reference_1core_s_per_sample"] = per_sample
