@@ -12,7 +12,7 @@ import common
 from oracle import refshim as R
 
 pkg = common.package()
-EMUL = os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
+EMUL = os.environ.get("HHE_EMUL_LIB") or os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
 BACKENDS = [pytest.param("emul"), pytest.param("cuda", marks=pytest.mark.gpu)]
 needs_ref = pytest.mark.skipif(not R.available(), reason="oracle/_ref/libhhe_ref.so not built")
 

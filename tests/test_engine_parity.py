@@ -16,7 +16,7 @@ from oracle import oracle as O
 
 pkg = common.package()
 FX = np.load(os.path.join(common.ROOT, "tests", "golden", "pasta_n512.npz"))
-EMUL = os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
+EMUL = os.environ.get("HHE_EMUL_LIB") or os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")  # tools/asan_emul.sh: the ASan build
 BACKENDS = [pytest.param("emul"), pytest.param("cuda", marks=pytest.mark.gpu)]
 N = 1024
 BSGS_STEPS = (-16, -32, -48, -64, -80, -96, -112)

@@ -17,7 +17,7 @@ from oracle import refshim as R
 pkg = common.package()
 seal_io = __import__("importlib").import_module(common.PKG + ".seal_io")
 pytestmark = pytest.mark.skipif(not R.available(), reason="oracle/_ref not built")
-EMUL = os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
+EMUL = os.environ.get("HHE_EMUL_LIB") or os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so")
 N = 1024
 Q = common.small_params(N, 3, 48)
 STEPS = (0, -1, 128)
