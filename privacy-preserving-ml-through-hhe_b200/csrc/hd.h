@@ -21,6 +21,19 @@
 #define FOR_THREADS(tid, nt) for (int tid = threadIdx.x, hhe_once_ = 1; hhe_once_; hhe_once_ = 0)
 #define SYNC() __syncthreads()
 #define SYNCWARP() __syncwarp()
+#elif defined(HHE_EMUL_ORDER) && HHE_EMUL_ORDER == 1
+// race check of the emulation harness (tools/order_emul.sh): the threads of a phase run in DESCENDING order ...
+#define FOR_THREADS(tid, nt) for (int hhe_i_ = (nt)-1, tid = hhe_i_; hhe_i_ >= 0; tid = --hhe_i_)
+#define SYNC() ((void)0)
+#define SYNCWARP() ((void)0)
+#elif defined(HHE_EMUL_ORDER) && HHE_EMUL_ORDER == 2
+// ... or in a scrambled order (odd multiplier modulo a power-of-two CTA size; ascending otherwise): a phase whose result depends on
+// the order of its threads (a missing barrier between a write and another thread's read) no longer matches the oracle
+#define FOR_THREADS(tid, nt)                                                                                                       \
+  for (int hhe_i_ = 0, hhe_p_ = (((nt) & ((nt)-1)) == 0), tid = hhe_p_ ? (11 & ((nt)-1)) : 0; hhe_i_ < (nt);                       \
+       ++hhe_i_, tid = hhe_p_ ? ((hhe_i_ * 37 + 11) & ((nt)-1)) : hhe_i_)
+#define SYNC() ((void)0)
+#define SYNCWARP() ((void)0)
 #else
 #define FOR_THREADS(tid, nt) for (int tid = 0; tid < (nt); ++tid)
 #define SYNC() ((void)0)
