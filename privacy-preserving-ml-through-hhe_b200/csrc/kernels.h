@@ -1577,11 +1577,11 @@ struct BehzExtendBody {
         const u32 r = mt * C->neg_inv_q_mt;
         for (int bb = 0; bb <= L; ++bb) {
           const DevMod mb = C->mod[C->K + bb];
-          u64 s = 0;
-          for (int i = 0; i < L; ++i) s = mul_add_mod(z[i], C->q2bsk[bb][i], s, mb);
+          Acc128 s;  // one reduction per output residue (modarith.h)
+          for (int i = 0; i < L; ++i) s.mac(z[i], C->q2bsk[bb][i]);
           const u64 rp = r >= 0x80000000u ? mb.q - (0x100000000ULL - r) : r;
-          const u64 v = mul_add_mod(rp, C->q_mod_bsk[bb], s, mb);
-          xb[(p * (L + 1) + bb) * N + j] = mul_shoup(v, C->inv_mt_bsk[bb], mb.q);
+          s.mac(rp, C->q_mod_bsk[bb]);
+          xb[(p * (L + 1) + bb) * N + j] = mul_shoup(s.reduce(mb), C->inv_mt_bsk[bb], mb.q);
         }
       }
     }
@@ -1637,26 +1637,29 @@ struct BehzScaleRoundBody {
         for (int i = 0; i < L; ++i) z[i] = mul_shoup(dq[(p * L + i) * N + j], C->t_ipq[i], C->mod[i].q);
         for (int bb = 0; bb <= L; ++bb) {
           const DevMod mb = C->mod[K + bb];
-          u64 s = 0;
-          for (int i = 0; i < L; ++i) s = mul_add_mod(z[i], C->q2bsk[bb][i], s, mb);
+          Acc128 s;  // one reduction per inner product (modarith.h)
+          for (int i = 0; i < L; ++i) s.mac(z[i], C->q2bsk[bb][i]);
           const u64 tb = mul_shoup(db[(p * (L + 1) + bb) * N + j], C->t_mod_bsk[bb], mb.q);
-          f[bb] = mul_shoup(sub_mod(tb, s, mb.q), C->inv_q_bsk[bb], mb.q);
+          f[bb] = mul_shoup(sub_mod(tb, s.reduce(mb), mb.q), C->inv_q_bsk[bb], mb.q);
         }
         const u64 f_sk = f[L];
         const DevMod msk = C->mod[K + L];
-        u64 sk = 0;
+        Acc128 sk;
         for (int i = 0; i < L; ++i) {
           f[i] = mul_shoup(f[i], C->inv_punct_b[i], C->mod[K + i].q);
-          sk = mul_add_mod(f[i], C->b2msk[i], sk, msk);
+          sk.mac(f[i], C->b2msk[i]);
         }
-        const u64 alpha = mul_shoup(sub_mod(sk, f_sk, msk.q), C->inv_pb_msk, msk.q);
+        const u64 alpha = mul_shoup(sub_mod(sk.reduce(msk), f_sk, msk.q), C->inv_pb_msk, msk.q);
         const bool upper = alpha > (msk.q >> 1);
         for (int jq = 0; jq < L; ++jq) {
           const DevMod mq = C->mod[jq];
-          u64 s = 0;
-          for (int i = 0; i < L; ++i) s = mul_add_mod(f[i], C->b2q[jq][i], s, mq);
-          s = upper ? mul_add_mod(msk.q - alpha, C->pb_mod_q[jq], s, mq) : mul_add_mod(alpha, mq.q - C->pb_mod_q[jq], s, mq);
-          out[(p * L + jq) * N + j] = s;
+          Acc128 s;
+          for (int i = 0; i < L; ++i) s.mac(f[i], C->b2q[jq][i]);
+          if (upper)
+            s.mac(msk.q - alpha, C->pb_mod_q[jq]);
+          else
+            s.mac(alpha, mq.q - C->pb_mod_q[jq]);
+          out[(p * L + jq) * N + j] = s.reduce(mq);
         }
       }
     }

@@ -82,4 +82,18 @@ HD u64 mul_add_mod(u64 a, u64 b, u64 c, const DevMod &m) {
   return barrett128(lo, hi, m);
 }
 
+// Sum of up to 32 products of residues (each factor < 2^61) kept as a 128-bit integer and reduced ONCE: the inner products of the
+// BEHZ base conversions (sum_i z_i * c_i mod m) cost one multiplication per term instead of a multiplication plus a 128-bit Barrett
+// reduction per term. 32 * 2^122 < 2^128, so the accumulator cannot overflow.
+struct Acc128 {
+  u64 lo = 0, hi = 0;
+  HD void mac(u64 a, u64 b) {
+    const u64 pl = a * b;
+    lo += pl;
+    hi += mulhi64(a, b) + (lo < pl);
+  }
+  // (hi:lo) mod q for ANY 128-bit value: hi is reduced first so that barrett128's precondition (hi < q) holds
+  HD u64 reduce(const DevMod &m) const { return barrett128(lo, barrett64(hi, m), m); }
+};
+
 }  // namespace hhe
