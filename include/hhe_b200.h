@@ -104,7 +104,9 @@ int hhe_exponentiate3(hhe_ctx *ctx, const uint64_t *a, uint64_t *out, size_t cou
  * out: ceil(n/128) size-2 ciphertexts. Galois keys are taken from HHE_KEYSET_0, relin key from HHE_RELIN. */
 int hhe_pasta3_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words, uint64_t nonce,
                          uint64_t first_counter, int use_bsgs, uint64_t *out);
-/* Same, for `records` independent records of n_words each that all restart at first_counter (CSP.cpp:247-252). */
+/* Same, for `records` independent records of n_words each that all restart at first_counter (CSP.cpp:247-252). The keystream
+ * ciphertext of a counter does not depend on the data and the evaluation is deterministic, so it is evaluated once per distinct
+ * counter per call and shared by the records (bit-identical to per-record evaluation; HHE_NO_SHARED_KEYSTREAM=1 turns it off). */
 int hhe_pasta3_decompose_records(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym_ct, size_t n_words,
                                  size_t records, uint64_t nonce, uint64_t first_counter, int use_bsgs, uint64_t *out);
 int hhe_mask(hhe_ctx *ctx, const uint64_t *a, const uint64_t *mask, size_t n_mask, uint64_t *out, size_t count);

@@ -419,13 +419,31 @@ static void decompose_host(Engine &e, const uint64_t *enc_key, const uint64_t *s
   u64 *d_sym = up(e, sym.data(), nblocks * kPastaT);
   u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nblocks + 1) / 2));
   e.dev().h2d(d_lens, lens.data(), nblocks * 4);
+  // records restart their counters: the bpr keystream ciphertexts are the same for every record and are computed once per call
+  // (Engine::pasta_keystreams); every block then only subtracts its keystream from its own encoded words
+  u64 *d_ks = nullptr;
+  u32 *d_idx = nullptr;
+  if (records > 1 && e.share_keystreams()) {
+    std::vector<u64> uniq(counters.begin(), counters.begin() + bpr);
+    std::vector<u32> idx(nblocks);
+    for (size_t blk = 0; blk < nblocks; ++blk) idx[blk] = static_cast<u32>(blk % bpr);
+    d_ks = e.scratch(bpr * ctw);
+    e.pasta_keystreams(d_key, uniq, nonce, use_bsgs != 0, d_ks);
+    d_idx = reinterpret_cast<u32 *>(e.scratch((nblocks + 1) / 2));
+    e.dev().h2d(d_idx, idx.data(), nblocks * 4);
+    e.dev().sync();
+  }
   OverlappedOut oo(e, std::min(step, nblocks) * ctw, nblocks > step);
   size_t chunk = 0;
   chunked(e, nblocks, [&](size_t off, size_t nb) {
     Engine::Scope inner(e);
     u64 *d_out = oo.buf(chunk);
-    std::vector<u64> ctr(counters.begin() + off, counters.begin() + off + nb);
-    e.pasta_decompose(d_key, d_sym + off * kPastaT, d_lens + off, ctr, nonce, use_bsgs != 0, d_out);
+    if (d_ks) {
+      e.pasta_finish(d_ks, d_idx + off, d_sym + off * kPastaT, d_lens + off, nb, d_out);
+    } else {
+      std::vector<u64> ctr(counters.begin() + off, counters.begin() + off + nb);
+      e.pasta_decompose(d_key, d_sym + off * kPastaT, d_lens + off, ctr, nonce, use_bsgs != 0, d_out);
+    }
     oo.send(chunk++, out + off * ctw, nb * ctw);
   });
   oo.finish();
@@ -463,6 +481,14 @@ int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym
       std::vector<u64> ones(rem, 1);
       d_ones = up(e, ones.data(), rem);
     }
+    // every record uses counters 0 .. bpr-1: their keystream ciphertexts are computed once for the whole call
+    u64 *d_ks = nullptr;
+    if (records > 1 && e.share_keystreams()) {
+      std::vector<u64> uniq(bpr);
+      for (size_t b = 0; b < bpr; ++b) uniq[b] = b;
+      d_ks = e.scratch(bpr * ctw);
+      e.pasta_keystreams(d_key, uniq, nonce, use_bsgs != 0, d_ks);
+    }
     // chunk over whole records so a chunk's blocks can be flattened on the device
     const size_t rec_per_chunk = std::max<size_t>(1, static_cast<size_t>(e.batch_limit()) / bpr);
     OverlappedOut oo(e, std::min(rec_per_chunk, records) * ctw, records > rec_per_chunk);
@@ -483,7 +509,16 @@ int hhe_csp_decompose(hhe_ctx *ctx, const uint64_t *enc_key, const uint64_t *sym
       u32 *d_lens = reinterpret_cast<u32 *>(e.scratch((nb + 1) / 2));
       e.dev().h2d(d_lens, lens.data(), nb * 4);
       u64 *d_blocks = e.scratch(nb * ctw), *d_flat = oo.buf(chunk);
-      e.pasta_decompose(d_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_blocks);
+      if (d_ks) {
+        std::vector<u32> idx(nb);
+        for (size_t blk = 0; blk < nb; ++blk) idx[blk] = static_cast<u32>(blk % bpr);
+        u32 *d_idx = reinterpret_cast<u32 *>(e.scratch((nb + 1) / 2));
+        e.dev().h2d(d_idx, idx.data(), nb * 4);
+        e.dev().sync();
+        e.pasta_finish(d_ks, d_idx, d_sym, d_lens, nb, d_blocks);
+      } else {
+        e.pasta_decompose(d_key, d_sym, d_lens, ctr, nonce, use_bsgs != 0, d_blocks);
+      }
       if (d_ones) {  // mask the last block of every record in place
         u64 *last = e.scratch(nr * ctw), *masked = e.scratch(nr * ctw);
         e.strided_copy(d_blocks + (bpr - 1) * ctw, bpr * ctw, last, ctw, ctw, nr);

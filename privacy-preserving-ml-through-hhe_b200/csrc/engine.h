@@ -50,7 +50,8 @@ class Engine {
            size_t limb_stride = 0);
   void add(const u64 *a, const u64 *b, u64 *out, size_t items, int size = 2);
   void negate(const u64 *a, u64 *out, size_t items);
-  void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx = nullptr);
+  void add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx = nullptr,
+                 const u32 *aidx = nullptr);
   void broadcast(const u64 *src, u64 *out, size_t words, size_t items);
   void encode_slots(const u64 *slots, size_t sstride, const u32 *lens, u32 n, u64 *pt, size_t items);
   // ndiag > 1: `ndiag` consecutive diagonals diag, diag + 1, ... in one launch, pt laid out [ndiag][items][N]
@@ -78,6 +79,11 @@ class Engine {
   void material(const u64 *d_counters, size_t nblocks, u64 nonce, u32 *d_out);
   void pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const std::vector<u64> &counters,
                        u64 nonce, bool use_bsgs, u64 *d_out);
+  // repeated counters: the keystream ciphertext once per distinct counter, then what is each block's own (engine_pasta.cu)
+  bool share_keystreams() const;
+  void pasta_keystreams(const u64 *d_enc_key, const std::vector<u64> &counters, u64 nonce, bool use_bsgs, u64 *d_ks);
+  void pasta_finish(const u64 *d_ks, const u32 *d_idx, const u64 *d_sym, const u32 *d_lens, size_t nblocks, u64 *d_out);
+  void pasta_check_keys();
   // plain PASTA-3 (PASTA::encrypt / decrypt): n_words words, block b uses counter first_counter + b
   void pasta_plain(const u64 *d_key256, const u64 *d_in, size_t n_words, u64 nonce, u64 first_counter, bool decrypt, u64 *d_out);
   void mask(const u64 *a, const u64 *d_mask_slots, u32 n, u64 *out, size_t items);

@@ -69,9 +69,10 @@ void Engine::negate(const u64 *a, u64 *out, size_t items) {
   dev_.launch(body, ew_grid(total), kEwThreads, 0);
 }
 
-void Engine::add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx) {
+void Engine::add_plain(const u64 *a, const u64 *pt, size_t pstride, u64 *out, size_t items, bool negate_first, const u32 *ptidx,
+                       const u32 *aidx) {
   const size_t total = items * ct_words();
-  AddPlainBody body{a, pt, pstride, out, dC_, negate_first ? 1 : 0, total, ptidx};
+  AddPlainBody body{a, pt, pstride, out, dC_, negate_first ? 1 : 0, total, ptidx, aidx};
   dev_.launch(body, ew_grid(total), kEwThreads, 0);
 }
 

@@ -265,22 +265,81 @@ void Engine::pasta_batch(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_le
       std::swap(state, tmp);
     }
   }
+  if (!d_sym) {  // keystream only: the caller finishes every block that uses it (pasta_decompose, shared keystreams)
+    dev_.d2d(d_out, state, nb * ctw * 8);
+    return;
+  }
   encode_slots(d_sym, kPastaT, d_lens, kPastaT, pt, nb);
   add_plain(state, pt, N, d_out, nb, true);  // negate_inplace; add_plain (:168-169)
 }
 
-void Engine::pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const std::vector<u64> &counters,
-                             u64 nonce, bool use_bsgs, u64 *d_out) {
-  const size_t nblocks = counters.size();
+void Engine::pasta_check_keys() {
   if (2 * kPastaT != P_.N && 4 * kPastaT > P_.N) throw std::runtime_error("too little slots for matmul implementation!");
   const u32 e1 = P_.galois_elt_from_step(-1), ec = static_cast<u32>(2 * P_.N - 1);
   need_key(0, e1);
   need_key(0, ec);
   need_key(2, 0);
   if (P_.N / 2 != kPastaT) need_key(0, P_.galois_elt_from_step(kPastaT));
+}
+
+bool Engine::share_keystreams() const { return !getenv_flag("HHE_NO_SHARED_KEYSTREAM"); }
+
+// The keystream ciphertext of a block depends on (encrypted key, nonce, counter) only -- not on the data -- and the evaluation is
+// deterministic. Records restart their counters (CSP.cpp:247-252), so within one call every block with the same
+// counter has the SAME keystream ciphertext, bit for bit: callers with repeated counters compute it once per distinct counter here
+// (d_ks[i] = the state of pasta_3_seal.cpp:106-167 for counters[i]) and finish every block with pasta_finish. A stream of distinct
+// counters (the headline workload) never takes this path.
+void Engine::pasta_keystreams(const u64 *d_enc_key, const std::vector<u64> &counters, u64 nonce, bool use_bsgs, u64 *d_ks) {
+  pasta_check_keys();
+  Scope sc(*this);
+  const size_t n = counters.size(), step = static_cast<size_t>(std::max(1, batch_)), ctw = ct_words();
+  u64 *d_ctr = scratch(std::min(step, std::max<size_t>(1, n)));
+  for (size_t off = 0; off < n; off += step) {
+    const size_t nb = std::min(step, n - off);
+    dev_.h2d(d_ctr, counters.data() + off, nb * 8);
+    pasta_batch(d_enc_key, nullptr, nullptr, d_ctr, nb, nb, nullptr, nonce, use_bsgs, d_ks + off * ctw);
+  }
+  dev_.sync();  // `counters` is the caller's host vector
+}
+
+// What is a block's own: res[b] = encode(c_b) - ks[idx[b]]  (negate_inplace + add_plain, pasta_3_seal.cpp:168-169)
+void Engine::pasta_finish(const u64 *d_ks, const u32 *d_idx, const u64 *d_sym, const u32 *d_lens, size_t nblocks, u64 *d_out) {
+  Scope sc(*this);
+  const size_t step = static_cast<size_t>(std::max(1, batch_)), ctw = ct_words(), N = P_.N;
+  u64 *pt = scratch(std::min(step, std::max<size_t>(1, nblocks)) * N);
+  for (size_t off = 0; off < nblocks; off += step) {
+    const size_t nb = std::min(step, nblocks - off);
+    encode_slots(d_sym + off * kPastaT, kPastaT, d_lens + off, kPastaT, pt, nb);
+    add_plain(d_ks, pt, N, d_out + off * ctw, nb, true, nullptr, d_idx + off);
+  }
+}
+
+void Engine::pasta_decompose(const u64 *d_enc_key, const u64 *d_sym, const u32 *d_lens, const std::vector<u64> &counters,
+                             u64 nonce, bool use_bsgs, u64 *d_out) {
+  const size_t nblocks = counters.size();
+  pasta_check_keys();
   Scope sc(*this);
   const size_t step = static_cast<size_t>(std::max(1, batch_)), ctw = ct_words();
   u64 *d_ctr = scratch(std::min(step, nblocks));
+  if (share_keystreams() && nblocks > 1) {  // see pasta_keystreams
+    std::map<u64, u32> seen;
+    std::vector<u64> uniq;
+    std::vector<u32> idx(nblocks);
+    for (size_t b = 0; b < nblocks; ++b) {
+      auto ins = seen.emplace(counters[b], static_cast<u32>(uniq.size()));
+      if (ins.second) uniq.push_back(counters[b]);
+      idx[b] = ins.first->second;
+    }
+    if (uniq.size() < nblocks) {
+      u64 *ks = scratch(uniq.size() * ctw);
+      pasta_keystreams(d_enc_key, uniq, nonce, use_bsgs, ks);
+      u32 *d_idx = reinterpret_cast<u32 *>(scratch((nblocks + 1) / 2));
+      dev_.h2d(d_idx, idx.data(), nblocks * 4);
+      pasta_finish(ks, d_idx, d_sym, d_lens, nblocks, d_out);
+      dev_.sync();  // idx is a host vector the copy above reads
+      return;
+    }
+  }
   // Blocks with equal SHAKE counters (records restart at counter 0: CSP.cpp:247-252) have identical round
   // matrices and constants: per lock-step batch the round material, the encoded diagonals and their lifted transforms are computed
   // once per DISTINCT counter, and every block reads its counter's copy through an index (didx).

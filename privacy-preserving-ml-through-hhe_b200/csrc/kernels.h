@@ -1168,6 +1168,7 @@ struct AddPlainBody {
   int negate;
   size_t total;  // count*2*L*N
   const u32 *ptidx;  // optional: item -> plaintext index (blocks sharing a SHAKE counter share round constants)
+  const u32 *aidx;   // optional: item -> ciphertext index in `a` (blocks sharing a SHAKE counter share the keystream ciphertext)
   HD void operator()(int bid, int nt, unsigned char *) const {
     const size_t N = C->N;
     const int L = C->L;
@@ -1180,7 +1181,7 @@ struct AddPlainBody {
         const size_t item = limb / static_cast<u32>(2 * L);
         const int comp = static_cast<int>((limb / static_cast<u32>(L)) & 1);
         const DevMod mi = C->mod[i];
-        u64 v = a[g];
+        u64 v = aidx ? a[(static_cast<size_t>(aidx[item]) * 2 * L + (limb % static_cast<u32>(2 * L))) * N + j] : a[g];
         if (negate) v = neg_mod(v, mi.q);
         if (comp == 0) {
           const u64 m = pt[(ptidx ? ptidx[item] : item) * pstride + j];

@@ -217,10 +217,15 @@ def test_transciphering_vs_oracle(eng, world, bsgs):
         assert np.array_equal(eng.pasta3_decompose(ek, sym[128:256], first_counter=1)[0], want[1])
 
 
+@pytest.mark.parametrize("shared_keystream", [True, False])
 @pytest.mark.parametrize("bsgs", [False, True])
-def test_records_sharing_one_counter(eng, world, bsgs):
-    """Records restart at counter 0 (CSP.cpp:247-252): a batch of one-block records shares its round
-    material, diagonals and their transforms. Same ciphertexts as transciphering each record on its own."""
+def test_records_sharing_one_counter(eng, world, bsgs, shared_keystream, monkeypatch):
+    """Records restart at counter 0 (CSP.cpp:247-252): the keystream ciphertext of a counter is the same for
+    every record and is computed once per call (default); with HHE_NO_SHARED_KEYSTREAM=1 every block is transciphered on its own
+    and the batch shares only its round material, diagonals and their transforms. Same ciphertexts either way as transciphering
+    each record on its own with the oracle."""
+    if not shared_keystream:
+        monkeypatch.setenv("HHE_NO_SHARED_KEYSTREAM", "1")
     o, keys, rng = world["orc"], world["keys"], np.random.default_rng(23)
     key = rng.integers(0, common.T, 256, dtype=np.uint64)
     ek = keys.encrypt_zero_plus(o, o.encode(common.pack_key(key, N)))
@@ -228,6 +233,12 @@ def test_records_sharing_one_counter(eng, world, bsgs):
     got = eng.pasta3_decompose(ek, np.concatenate(recs), use_bsgs=bsgs, records=3)
     for r in range(3):
         assert np.array_equal(got[r], o.pasta_decompose(ek, recs[r], use_bsgs=bsgs)[0]), r
+    # two-block records (counters 0, 1 per record, ragged last block): both keystreams shared by both records
+    recs2 = [O.pasta_plain(key, common.T, rng.integers(0, common.T, 150, dtype=np.uint64)) for _ in range(2)]
+    got2 = eng.pasta3_decompose(ek, np.concatenate(recs2), use_bsgs=bsgs, records=2).reshape(2, 2, 2, o.L, N)
+    for r in range(2):
+        want = o.pasta_decompose(ek, recs2[r], use_bsgs=bsgs)
+        assert np.array_equal(got2[r, 0], want[0]) and np.array_equal(got2[r, 1], want[1]), r
 
 
 # ---- golden vectors generated from the reference itself ---------------------------------------------------------------

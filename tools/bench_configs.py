@@ -185,6 +185,9 @@ def next_rows(ctx, ref, enc_key, key, rng, ref_ops, records=98, eval_samples=32,
     out["f1_service_handlers"] = {
         "csp_decompose": {"records": R_, "words_per_record": n, "records_per_s": R_ / dt, "blocks_per_s": 3 * R_ / dt,
                           "parity_records_decrypt_to_input": bool(ok), "reference_1core_s_per_record": ref_rec,
+                          "note": "every record uses counters 0..2: their three keystream ciphertexts are evaluated once per call and "
+                                  "shared by all records (bit-identical to per-record evaluation, HHE_NO_SHARED_KEYSTREAM=1 restores it: "
+                                  "52.7 records/s); what remains per record is encode + add_plain, mask, flatten and the copy-out",
                           "speedup_vs_1core": R_ / dt * ref_rec},
         "csp_evaluate_model": {"samples": S_, "row_length": n, "samples_per_s": S_ / dte, "parity_slot_equals_dot_product": bool(oke),
                                "noise_budget_left_bits": min(int(d[1]) for d in dece),
