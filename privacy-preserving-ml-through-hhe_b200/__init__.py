@@ -334,12 +334,20 @@ class Context:
         return o
 
     # -- hot path ---------------------------------------------------------------------------------------------
-    def pasta3_decompose(self, enc_key, sym_ct, use_bsgs=False, nonce=123456789, first_counter=0, records=1):
+    def _into(self, out, shape):
+        """Caller-owned result buffer (e.g. pinned host memory, reused between calls) or a fresh array"""
+        if out is None:
+            return np.zeros(shape, dtype=np.uint64)
+        if out.dtype != np.uint64 or not out.flags.c_contiguous or out.size != int(np.prod(shape)):
+            raise HheInvalidArgument(HHE_ERR_INVALID, "`out` must be a C-contiguous uint64 array of the result's size")
+        return out.reshape(shape)
+
+    def pasta3_decompose(self, enc_key, sym_ct, use_bsgs=False, nonce=123456789, first_counter=0, records=1, out=None):
         k, pk, _ = self._cts(enc_key)
         s = np.ascontiguousarray(sym_ct, dtype=np.uint64)
         n_words = s.size // records
         nblk = (n_words + 127) // 128
-        o = np.zeros((records * nblk, 2, self.L, self.N), dtype=np.uint64)
+        o = self._into(out, (records * nblk, 2, self.L, self.N))
         if records == 1:
             rc = self.lib.hhe_pasta3_decompose(self.h, pk, s.ctypes.data_as(_u64p), C.c_size_t(n_words), C.c_uint64(nonce),
                                                C.c_uint64(first_counter), int(use_bsgs), o.ctypes.data_as(_u64p))
@@ -370,10 +378,10 @@ class Context:
         self._chk(self.lib.hhe_vec_sum(self.h, pa, C.c_size_t(n), keys, o.ctypes.data_as(_u64p), C.c_size_t(cnt)))
         return o
 
-    def fc_rows(self, x, w, n, keys=KEYSET_1):
+    def fc_rows(self, x, w, n, keys=KEYSET_1, out=None):
         x, px, ns = self._cts(x)
         w, pw, nr = self._cts(w)
-        o = np.zeros((ns, nr, 2, self.L, self.N), dtype=np.uint64)
+        o = self._into(out, (ns, nr, 2, self.L, self.N))
         self._chk(self.lib.hhe_fc_rows(self.h, px, C.c_size_t(ns), pw, C.c_size_t(nr), C.c_size_t(n), keys, o.ctypes.data_as(_u64p)))
         return o
 

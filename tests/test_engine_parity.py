@@ -241,6 +241,21 @@ def test_records_sharing_one_counter(eng, world, bsgs, shared_keystream, monkeyp
         assert np.array_equal(got2[r, 0], want[0]) and np.array_equal(got2[r, 1], want[1]), r
 
 
+def test_caller_owned_result_buffers(eng, world):
+    """pasta3_decompose / fc_rows write into a caller-owned array (pinned memory in bench.py) when one is given"""
+    o, keys, rng = world["orc"], world["keys"], np.random.default_rng(29)
+    key = rng.integers(0, common.T, 256, dtype=np.uint64)
+    ek = keys.encrypt_zero_plus(o, o.encode(common.pack_key(key, N)))
+    sym = O.pasta_plain(key, common.T, rng.integers(0, common.T, 128, dtype=np.uint64))
+    buf = np.zeros((1, 2, o.L, N), dtype=np.uint64)
+    got = eng.pasta3_decompose(ek, sym, out=buf)
+    assert np.shares_memory(got, buf) and np.array_equal(buf, eng.pasta3_decompose(ek, sym))
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.pasta3_decompose(ek, sym, out=np.zeros(5, dtype=np.uint64))
+    with pytest.raises(pkg.HheInvalidArgument):
+        eng.pasta3_decompose(ek, sym, out=np.zeros((1, 2, o.L, N), dtype=np.int64))
+
+
 # ---- golden vectors generated from the reference itself ---------------------------------------------------------------
 @pytest.fixture(scope="module", params=BACKENDS)
 def eng512(request):

@@ -140,11 +140,13 @@ def config3(ctx, ref, enc_key, key, rng, peak, ref_ops, samples=1024, rank=0, wo
     return xs, w, syms, enc_w1
 
 
-def config3_run(ctx, enc_key, syms, enc_w1):
+def config3_run(ctx, enc_key, syms, enc_w1, bufs=None):
+    """decompose (records -> ciphertexts in host memory) then the FC layer on them (host in, host out), like the CSP's two handlers.
+    bufs: two caller-owned host arrays for the two results (bench.py passes pinned memory, reused between calls)."""
     S = syms.shape[0]
     t0 = time.perf_counter()
-    cts = ctx.pasta3_decompose(enc_key, syms.reshape(-1), records=S)
-    outs = ctx.fc_rows(cts, enc_w1, 128)
+    cts = ctx.pasta3_decompose(enc_key, syms.reshape(-1), records=S, out=None if bufs is None else bufs[0][:S])
+    outs = ctx.fc_rows(cts, enc_w1, 128, out=None if bufs is None else bufs[1][:S])
     return outs, time.perf_counter() - t0
 
 
