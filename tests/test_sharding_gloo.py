@@ -99,3 +99,47 @@ def test_gather_ciphertexts_ragged_shards(tmp_path):
     for p in procs:
         assert p.wait(timeout=300) == 0
     assert out.read_text() == "ok"
+
+
+RECORDS_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["HHE_ROOT"]); sys.path.insert(0, os.path.join(os.environ["HHE_ROOT"], "tests"))
+import common, importlib
+pkg = common.package(); shard = importlib.import_module(common.PKG + ".shard")
+fx = np.load(os.path.join(common.ROOT, "tests", "golden", "pasta_n512.npz"))
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["HHE_PORT"], rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+ctx = pkg.Context(int(fx["N"]), int(fx["t"]), fx["q"], lib_path=os.path.join(common.ROOT, "tests", "emul", "libhhe_emul.so"), emulation_harness=True)
+for name, kind in (("gk_m1", 0), ("gk_p128", 0), ("gk_col", 0), ("rk", 2)):
+    ctx.load_ksk(kind, int(fx[name + "_elt"]), fx[name])
+# 5 one-block records that all restart at counter 0 (the ECG batch of BASELINE configs[2]), sharded by record: 3 + 2
+R, n = 5, 100
+recs = np.random.default_rng(5).integers(0, int(fx["t"]), (R, n), dtype=np.uint64)
+lo, hi = shard.block_range(R, rank, world)
+mine = ctx.pasta3_decompose(fx["enc_key"], recs[lo:hi].reshape(-1), records=hi - lo)  # keystream shared by this rank's records
+got = shard.gather_ciphertexts(mine, world)
+if rank == 0:
+    whole = ctx.pasta3_decompose(fx["enc_key"], recs.reshape(-1), records=R)
+    single = np.stack([ctx.pasta3_decompose(fx["enc_key"], recs[r])[0] for r in range(R)])  # one call per record: no sharing at all
+    assert np.array_equal(got, whole) and np.array_equal(got, single)
+    open(os.environ["HHE_OUT"], "w").write("ok")
+dist.destroy_process_group()
+'''
+
+
+def test_records_sharded_over_two_ranks(tmp_path):
+    """Sample sharding (the `fc` line of bench.py at N > 1): records that restart their counters are split over the ranks, every rank
+    evaluates the shared keystream for its own call; the gathered ciphertexts equal the one-rank call and per-record calls bit for bit."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(common.ROOT, "tests", "emul")])
+    script = tmp_path / "records.py"
+    script.write_text(RECORDS_WORKER)
+    out = tmp_path / "ok.txt"
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", HHE_ROOT=common.ROOT, HHE_PORT="29655", HHE_OUT=str(out))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=900) == 0
+    assert out.read_text() == "ok"
